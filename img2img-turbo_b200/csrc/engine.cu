@@ -1,0 +1,805 @@
+// Engine implementation: weight store + load-time fold, op builders, executor.  The model graph lives in model.cu.
+#include "engine.cuh"
+
+#include <algorithm>
+
+namespace i2it {
+
+static inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+static inline int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+#define DISPATCH_T(dt, ...)                                   \
+  do {                                                        \
+    if ((dt) == DT_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else { using T = __half; __VA_ARGS__; }                   \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// TMA
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    I2IT_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    I2IT_CHECK(q == cudaDriverEntryPointSuccess && p != nullptr, "cuTensorMapEncodeTiled unavailable in this driver");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+CUtensorMap encode_tmap(const TmapSpec& s, int dtype) {
+  CUtensorMap m;
+  cuuint64_t dims[5], strides[4];
+  cuuint32_t box[5], es[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < 5; ++i) { dims[i] = s.dim[i]; box[i] = s.box[i]; }
+  for (int i = 0; i < 4; ++i) strides[i] = s.stride[i];
+  const CUtensorMapDataType dt = (dtype == DT_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = encode_fn()(&m, dt, 5, const_cast<void*>(s.base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[512];
+    snprintf(buf, sizeof buf,
+             "cuTensorMapEncodeTiled failed (%d): base=%p dim=(%llu,%llu,%llu,%llu,%llu) stride=(%llu,%llu,%llu,%llu) "
+             "box=(%u,%u,%u,%u,%u)", static_cast<int>(r), s.base, (unsigned long long)dims[0], (unsigned long long)dims[1],
+             (unsigned long long)dims[2], (unsigned long long)dims[3], (unsigned long long)dims[4],
+             (unsigned long long)strides[0], (unsigned long long)strides[1], (unsigned long long)strides[2],
+             (unsigned long long)strides[3], box[0], box[1], box[2], box[3], box[4]);
+    throw Error(buf);
+  }
+  return m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pool
+// ---------------------------------------------------------------------------------------------
+Pool::~Pool() {
+  for (auto& b : blocks) cudaFree(b.first);
+}
+void* Pool::get(size_t bytes, size_t* actual) {
+  bytes = (bytes + 511) / 512 * 512;
+  auto it = free_.lower_bound(bytes);
+  if (it != free_.end() && it->first <= bytes + bytes / 2 + (1u << 20)) {
+    void* p = it->second;
+    *actual = it->first;
+    free_.erase(it);
+    return p;
+  }
+  void* p = nullptr;
+  I2IT_CUDA(cudaMalloc(&p, bytes));
+  blocks.emplace_back(p, bytes);
+  total += bytes;
+  *actual = bytes;
+  return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// engine basics
+// ---------------------------------------------------------------------------------------------
+__global__ void cvt16_to_f32_kernel(const uint16_t* s, float* d, long long n, int is_bf16) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (is_bf16) d[i] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(s)[i]);
+  else d[i] = __half2float(reinterpret_cast<const __half*>(s)[i]);
+}
+
+Engine::Engine(const i2it_config& c) : cfg(c), dtype(c.dtype) {
+  I2IT_CHECK(c.dtype == DT_F16 || c.dtype == DT_BF16, "dtype must be I2IT_F16 or I2IT_BF16");
+  I2IT_CUDA(cudaSetDevice(c.device));
+  cudaDeviceProp prop;
+  I2IT_CUDA(cudaGetDeviceProperties(&prop, c.device));
+  I2IT_CHECK(prop.major == 10, "libi2it is built for sm_100a (B200) only; found compute capability " +
+                                   std::to_string(prop.major) + "." + std::to_string(prop.minor));
+  num_sms = prop.multiProcessorCount;
+  I2IT_CUDA(cudaFuncSetAttribute(tapgemm_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+  I2IT_CUDA(cudaFuncSetAttribute(tapgemm_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+  int* h = nullptr;
+  I2IT_CUDA(cudaHostAlloc(&h, sizeof(int), cudaHostAllocMapped));
+  *h = 0;
+  I2IT_CUDA(cudaHostGetDevicePointer(&d_err, h, 0));
+  err_host_ = h;
+  encode_fn();
+}
+
+Engine::~Engine() {
+  plans_.clear();
+  free_prepared();
+  for (auto& kv : w_) cudaFree(kv.second.d);
+  if (scratch_) cudaFree(scratch_);
+  if (err_host_) cudaFreeHost(err_host_);
+}
+
+void Engine::check_device_error() {
+  if (err_host_ && *err_host_ != 0) {
+    const int code = *err_host_;
+    throw Error("tapgemm watchdog tripped (pipeline stage code " + std::to_string(code) +
+                ": 1=producer/empty 2=mma/tmem_empty 3=mma/full 4=epilogue/tmem_full)");
+  }
+}
+
+void* Engine::dmalloc(size_t bytes) {
+  void* p = nullptr;
+  I2IT_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+  prep_allocs_.push_back(p);
+  return p;
+}
+
+void Engine::free_prepared() {
+  for (void* p : prep_allocs_) cudaFree(p);
+  prep_allocs_.clear();
+  prepared_.clear();
+  prepared_f32_.clear();
+  emb_act_ = nullptr;
+}
+
+void Engine::set_weight(const std::string& key_in, const void* data, const int64_t* shape, int ndim, int dt, bool is_dev) {
+  std::string key = key_in;
+  const std::string bl = ".base_layer.";
+  const size_t pos = key.find(bl);
+  if (pos != std::string::npos) key = key.substr(0, pos) + "." + key.substr(pos + bl.size());
+  WT t;
+  t.numel = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); t.numel *= shape[i]; }
+  I2IT_CHECK(t.numel > 0, "empty tensor for key " + key);
+  I2IT_CUDA(cudaMalloc(&t.d, t.numel * sizeof(float)));
+  if (dt == DT_F32) {
+    I2IT_CUDA(cudaMemcpy(t.d, data, t.numel * sizeof(float), is_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  } else {
+    I2IT_CHECK(dt == DT_F16 || dt == DT_BF16, "unsupported weight dtype");
+    uint16_t* tmp = nullptr;
+    I2IT_CUDA(cudaMalloc(&tmp, t.numel * 2));
+    I2IT_CUDA(cudaMemcpy(tmp, data, t.numel * 2, is_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    cvt16_to_f32_kernel<<<ceil_div(t.numel, 256), 256>>>(tmp, t.d, t.numel, dt == DT_BF16);
+    I2IT_CUDA(cudaDeviceSynchronize());
+    cudaFree(tmp);
+  }
+  auto it = w_.find(key);
+  if (it != w_.end()) { cudaFree(it->second.d); w_.erase(it); }
+  w_.emplace(key, std::move(t));
+  finalized_ = false;
+}
+
+bool Engine::has(const std::string& key) const { return w_.count(key) != 0; }
+
+const WT& Engine::raw(const std::string& name, const char* what) const {
+  auto it = w_.find(name + "." + what);
+  I2IT_CHECK(it != w_.end(), "missing weight '" + name + "." + what + "'");
+  return it->second;
+}
+
+float Engine::adapter_weight(const std::string& name, const std::string& adapter) const {
+  auto it = adapter_scale_.find(adapter);
+  I2IT_CHECK(it != adapter_scale_.end(), "no scale registered for LoRA adapter '" + adapter + "' (layer " + name + ")");
+  const bool is_unet = name.rfind("unet.", 0) == 0;
+  return it->second * (is_unet ? lw_unet_ : lw_vae_);
+}
+
+void Engine::finalize(float lw_unet, float lw_vae, float skip_gamma, float twin_r) {
+  I2IT_CUDA(cudaDeviceSynchronize());
+  lw_unet_ = lw_unet; lw_vae_ = lw_vae; skip_gamma_ = skip_gamma; twin_r_ = twin_r;
+  plans_.clear();
+  last_plan_ = nullptr;
+  free_prepared();
+  finalized_ = true;
+}
+
+// acc (fp32 scratch) = c0*W (+ c1*W_other) + sum_adapters s_a * B_a @ A_a
+float* Engine::fold_f32(const std::string& name, long long* numel, float c0, const std::string& other, float c1) {
+  const WT& w = raw(name, "weight");
+  if (w.numel > scratch_n_) {
+    if (scratch_) cudaFree(scratch_);
+    scratch_n_ = std::max<long long>(w.numel, 1ll << 24);
+    I2IT_CUDA(cudaMalloc(&scratch_, scratch_n_ * sizeof(float)));
+  }
+  const float* w1 = nullptr;
+  if (!other.empty()) {
+    const WT& o = raw(other, "weight");
+    I2IT_CHECK(o.numel == w.numel, "TwinConv shapes differ");
+    w1 = o.d;
+  }
+  wprep_init_kernel<<<ceil_div(w.numel, 256), 256>>>(scratch_, w.d, c0, w1, c1, w.numel);
+  const std::string pre = name + ".lora_A.";
+  for (const auto& kv : w_) {
+    if (kv.first.compare(0, pre.size(), pre) != 0) continue;
+    const std::string rest = kv.first.substr(pre.size());            // "<adapter>.weight"
+    const size_t dot = rest.rfind('.');
+    const std::string adapter = rest.substr(0, dot);
+    const float s = adapter_weight(name, adapter);
+    if (s == 0.f) continue;
+    const WT& A = kv.second;
+    auto itb = w_.find(name + ".lora_B." + adapter + ".weight");
+    I2IT_CHECK(itb != w_.end(), "lora_A without lora_B for " + name);
+    const WT& Bm = itb->second;
+    const int rank = static_cast<int>(A.shape[0]);
+    const long long inner = A.numel / rank;
+    I2IT_CHECK(Bm.shape[0] * inner == w.numel && Bm.shape[1] == rank, "LoRA shape mismatch at " + name);
+    wprep_lora_kernel<<<ceil_div(w.numel, 256), 256>>>(scratch_, A.d, Bm.d, s, rank, inner, w.numel);
+  }
+  I2IT_CUDA(cudaGetLastError());
+  *numel = w.numel;
+  return scratch_;
+}
+
+PW Engine::prep(const std::string& cache_key, const std::vector<std::string>& names, bool geglu, float scale,
+                const float* bias_add) {
+  auto it = prepared_.find(cache_key);
+  if (it != prepared_.end()) return it->second;
+  I2IT_CHECK(finalized_, "i2it_finalize_weights must be called before a forward");
+  PW pw;
+  const WT& w0 = raw(names[0], "weight");
+  pw.cin = static_cast<int>(w0.shape[1]);
+  pw.taps = (w0.shape.size() == 4) ? static_cast<int>(w0.shape[2] * w0.shape[3]) : 1;
+  pw.cin_pad = round_up(pw.cin, 8);
+  bool any_bias = bias_add != nullptr;
+  for (const auto& n : names) {
+    const WT& w = raw(n, "weight");
+    I2IT_CHECK(static_cast<int>(w.shape[1]) == pw.cin, "fused projection with different input widths: " + n);
+    pw.rows += static_cast<int>(w.shape[0]);
+    any_bias = any_bias || has(n + ".bias");
+  }
+  I2IT_CHECK(!geglu || names.size() == 1, "GEGLU interleave applies to a single projection");
+  const size_t wbytes = static_cast<size_t>(pw.taps) * pw.rows * pw.cin_pad * 2;
+  pw.w = static_cast<uint16_t*>(dmalloc(wbytes));
+  if (any_bias) {
+    pw.bias = static_cast<float*>(dmalloc(pw.rows * sizeof(float)));
+    I2IT_CUDA(cudaMemset(pw.bias, 0, pw.rows * sizeof(float)));
+  }
+  int row_off = 0;
+  for (const auto& n : names) {
+    long long numel = 0;
+    float* acc = fold_f32(n, &numel);
+    const int cout = static_cast<int>(raw(n, "weight").shape[0]);
+    const long long total = static_cast<long long>(cout) * pw.cin_pad * pw.taps;
+    const int half = geglu ? cout / 2 : 0;
+    DISPATCH_T(dtype, (wprep_store_kernel<T><<<ceil_div(total, 256), 256>>>(
+                          acc, reinterpret_cast<T*>(pw.w), cout, pw.cin, pw.taps, pw.cin_pad, pw.rows, row_off, half,
+                          scale, total)));
+    if (pw.bias) {
+      const float* b = has(n + ".bias") ? raw(n, "bias").d : nullptr;
+      bias_store_kernel<<<ceil_div(cout, 256), 256>>>(b, pw.bias, cout, row_off, half, bias_add);
+    }
+    row_off += cout;
+  }
+  I2IT_CUDA(cudaGetLastError());
+  prepared_[cache_key] = pw;
+  return pw;
+}
+
+PW Engine::prep_twin(const std::string& pre, const std::string& cur, float r) {
+  const std::string key = pre + "|twin";
+  auto it = prepared_.find(key);
+  if (it != prepared_.end()) return it->second;
+  I2IT_CHECK(r >= 0.f, "the state dict has a TwinConv conv_in but no blend ratio r was given (deterministic forward on a "
+                       "sketch_to_image_stochastic model is undefined in the reference too)");
+  PW pw;
+  const WT& w0 = raw(pre, "weight");
+  pw.rows = static_cast<int>(w0.shape[0]);
+  pw.cin = static_cast<int>(w0.shape[1]);
+  pw.taps = static_cast<int>(w0.shape[2] * w0.shape[3]);
+  pw.cin_pad = round_up(pw.cin, 8);
+  pw.w = static_cast<uint16_t*>(dmalloc(static_cast<size_t>(pw.taps) * pw.rows * pw.cin_pad * 2));
+  pw.bias = static_cast<float*>(dmalloc(pw.rows * sizeof(float)));
+  long long numel = 0;
+  float* acc = fold_f32(pre, &numel, 1.f - r, cur, r);
+  const long long total = static_cast<long long>(pw.rows) * pw.cin_pad * pw.taps;
+  DISPATCH_T(dtype, (wprep_store_kernel<T><<<ceil_div(total, 256), 256>>>(acc, reinterpret_cast<T*>(pw.w), pw.rows, pw.cin,
+                                                                         pw.taps, pw.cin_pad, pw.rows, 0, 0, 1.f, total)));
+  // bias = (1-r) b_pre + r b_cur
+  wprep_init_kernel<<<ceil_div(pw.rows, 256), 256>>>(pw.bias, raw(pre, "bias").d, 1.f - r, raw(cur, "bias").d, r, pw.rows);
+  I2IT_CUDA(cudaGetLastError());
+  prepared_[key] = pw;
+  return pw;
+}
+
+NormW Engine::norm(const std::string& name) {
+  NormW n;
+  const WT& g = raw(name, "weight");
+  n.g = g.d;
+  n.b = raw(name, "bias").d;
+  n.C = static_cast<int>(g.numel);
+  return n;
+}
+
+const float* Engine::temb_bias(const std::string& p) {
+  const std::string key = p + "|temb";
+  auto it = prepared_f32_.find(key);
+  if (it != prepared_f32_.end()) return it->second;
+  const int T = cfg.temb_dim, C0 = cfg.unet_channels[0];
+  if (!emb_act_) {
+    // Timesteps(flip_sin_to_cos=True, freq_shift=0) at t = 999, then TimestepEmbedding, then the SiLU every resnet applies
+    std::vector<float> te(C0);
+    const int half = C0 / 2;
+    for (int i = 0; i < half; ++i) {
+      const float f = expf(-logf(10000.f) * static_cast<float>(i) / static_cast<float>(half));
+      te[i] = cosf(999.f * f);
+      te[half + i] = sinf(999.f * f);
+    }
+    float* d_te = static_cast<float*>(dmalloc(C0 * sizeof(float)));
+    float* d_h = static_cast<float*>(dmalloc(T * sizeof(float)));
+    emb_act_ = static_cast<float*>(dmalloc(T * sizeof(float)));
+    I2IT_CUDA(cudaMemcpy(d_te, te.data(), C0 * sizeof(float), cudaMemcpyHostToDevice));
+    long long n = 0;
+    float* W1 = fold_f32("unet.time_embedding.linear_1", &n);
+    gemv_kernel<<<ceil_div(T * 32ll, 256), 256>>>(W1, raw("unet.time_embedding.linear_1", "bias").d, d_te, d_h, T, C0, 1);
+    float* W2 = fold_f32("unet.time_embedding.linear_2", &n);
+    gemv_kernel<<<ceil_div(T * 32ll, 256), 256>>>(W2, raw("unet.time_embedding.linear_2", "bias").d, d_h, emb_act_, T, T, 1);
+  }
+  const WT& w = raw(p + ".time_emb_proj", "weight");
+  const int cout = static_cast<int>(w.shape[0]);
+  float* out = static_cast<float*>(dmalloc(cout * sizeof(float)));
+  long long n = 0;
+  float* W = fold_f32(p + ".time_emb_proj", &n);
+  gemv_kernel<<<ceil_div(cout * 32ll, 256), 256>>>(W, raw(p + ".time_emb_proj", "bias").d, emb_act_, out, cout, T, 0);
+  I2IT_CUDA(cudaGetLastError());
+  prepared_f32_[key] = out;
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// op builders
+// ---------------------------------------------------------------------------------------------
+std::shared_ptr<void> Engine::alloc_raw(Plan& P, size_t bytes) {
+  size_t actual = 0;
+  void* p = P.pool.get(bytes, &actual);
+  Pool* pool = &P.pool;
+  return std::shared_ptr<void>(p, [pool, actual](void* q) { pool->put(q, actual); });
+}
+
+Act Engine::alloc_act(Plan& P, int N, int H, int W, int C, int ld, bool zero_persistent) {
+  Act a;
+  a.N = N; a.H = H; a.W = W; a.C = C; a.ld = ld ? ld : C;
+  const size_t bytes = static_cast<size_t>(N) * H * W * a.ld * 2;
+  a.hold = alloc_raw(P, bytes);
+  a.p = static_cast<uint16_t*>(a.hold.get());
+  if (zero_persistent) {
+    I2IT_CUDA(cudaMemset(a.p, 0, bytes));
+    P.keep.push_back(a.hold);      // never returns to the pool: the zero padding must survive
+  }
+  return a;
+}
+
+int Engine::pick_bn(long long m_tiles, int N, bool) const {
+  if (N <= 16) return 16;
+  static const int cand[] = {256, 224, 192, 160, 128, 112, 96, 80, 64, 48, 32, 16};
+  int best = 16;
+  double best_cost = 1e30;
+  for (int bn : cand) {
+    if (bn > round_up(N, 16)) continue;
+    const long long tiles = m_tiles * ceil_div(N, bn);
+    const long long waves = (tiles + num_sms - 1) / num_sms;
+    const double cost = static_cast<double>(waves) * (std::max(bn, 64) + 24);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+void Engine::launch_gemm(Plan& P, const CUtensorMap& ta, const CUtensorMap& tb, const TapGemmParams& p, int grid,
+                         bool out_from_io) {
+  const int dt = dtype;
+  Plan* plan = &P;
+  add_op(P, [ta, tb, p, grid, dt, out_from_io, plan](cudaStream_t st) {
+    TapGemmParams q = p;
+    if (out_from_io) q.out = plan->io.out;
+    DISPATCH_T(dt, (tapgemm_kernel<T><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, q)));
+  });
+}
+
+static void fill_strides(TmapSpec& s) {
+  // size-1 dims still need a legal (16-byte multiple) stride
+  for (int i = 0; i < 4; ++i)
+    if (s.stride[i] == 0 || (s.stride[i] % 16) != 0) s.stride[i] = 16;
+}
+
+Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o) {
+  const int k = o.ksize, taps = k * k;
+  I2IT_CHECK(w.taps == taps, "conv: weight taps mismatch");
+  I2IT_CHECK(x.C == w.cin || x.C == w.cin_pad, "conv: input channels " + std::to_string(x.C) + " vs weight " +
+                                                  std::to_string(w.cin));
+  I2IT_CHECK(x.ld % 8 == 0, "conv: pixel stride must be a multiple of 8 elements");
+  const int Ho = x.H / o.stride, Wo = x.W / o.stride;
+  const int gemm_n = w.rows;
+  const int outc = (o.act == TG_ACT_GEGLU) ? gemm_n / 2 : gemm_n;
+
+  Act out;
+  if (o.out) {
+    out = *o.out;
+  } else if (!o.to_io_out_nchw) {
+    I2IT_CHECK(!o.out_fp32, "conv: fp32 output needs an explicit out view");
+    const int ld = round_up(outc, 8);
+    const bool small = (outc % 8) != 0;
+    out = alloc_act(P, x.N, Ho, Wo, small ? ld : outc, ld, small);
+  }
+
+  TmapSpec sa, sb;
+  TapGemmParams p;
+  std::memset(&p, 0, sizeof p);
+  int tw, th, tn;
+  const long long ldo = o.to_io_out_nchw ? 0 : out.ld;
+  if (o.stride == 1) {
+    tw = (x.H == 1) ? std::min(128, pow2ceil(x.W)) : std::min(o.to_io_out_nchw ? 32 : 16, pow2ceil(x.W));
+    th = std::min(128 / tw, pow2ceil(x.H));
+    tn = 128 / (tw * th);
+    sa.base = x.p;
+    sa.dim[0] = x.C; sa.dim[1] = x.W; sa.dim[2] = x.H; sa.dim[3] = x.N; sa.dim[4] = 1;
+    sa.stride[0] = x.ld * 2ull; sa.stride[1] = 2ull * x.W * x.ld; sa.stride[2] = 2ull * x.H * x.W * x.ld;
+    sa.stride[3] = sa.stride[2];
+    sa.box[0] = 64; sa.box[1] = tw; sa.box[2] = th; sa.box[3] = tn; sa.box[4] = 1;
+    p.tdim[0] = ceil_div(x.W, tw); p.tdim[1] = ceil_div(x.H, th); p.tdim[2] = ceil_div(x.N, tn); p.tdim[3] = 1;
+    p.box[0] = tw; p.box[1] = th; p.box[2] = tn; p.box[3] = 1;
+    p.ext[0] = Wo; p.ext[1] = Ho; p.ext[2] = x.N; p.ext[3] = 1;
+    p.a_mul[0] = tw; p.a_mul[1] = th; p.a_mul[2] = tn; p.a_mul[3] = 0;
+    const int pad = k / 2;
+    for (int ky = 0; ky < k; ++ky)
+      for (int kx = 0; kx < k; ++kx) {
+        const int t = ky * k + kx;
+        p.tap_a[t][0] = 0; p.tap_a[t][1] = kx - pad; p.tap_a[t][2] = ky - pad; p.tap_a[t][3] = 0; p.tap_a[t][4] = 0;
+        p.tap_b[t][0] = 0; p.tap_b[t][1] = t; p.tap_b[t][2] = 0; p.tap_b[t][3] = 0;
+      }
+    p.ostride[0] = ldo; p.ostride[1] = static_cast<long long>(Wo) * ldo;
+    p.ostride[2] = static_cast<long long>(Ho) * Wo * ldo; p.ostride[3] = 0;
+    p.kchunks = ceil_div(x.C, 64);
+  } else {
+    I2IT_CHECK(o.stride == 2 && k == 3, "conv: only 3x3 stride-2 is on the path");
+    I2IT_CHECK(x.ld == x.C && x.C % 64 == 0 && x.H % 2 == 0 && x.W % 2 == 0, "conv s2: needs dense NHWC, C%64==0, even H/W");
+    tw = std::min(16, pow2ceil(Wo));
+    th = std::min(128 / tw, pow2ceil(Ho));
+    tn = 128 / (tw * th);
+    const unsigned long long C = x.C;
+    // 5-D view (px*C + c, xo, py, yo, n) of the dense NHWC input: a stride-2 tap is a plain box in this view
+    sa.base = x.p;
+    sa.dim[0] = 2 * C; sa.dim[1] = Wo; sa.dim[2] = 2; sa.dim[3] = Ho; sa.dim[4] = x.N;
+    sa.stride[0] = 2 * C * 2; sa.stride[1] = x.W * C * 2; sa.stride[2] = 2ull * x.W * C * 2; sa.stride[3] = 1ull * x.H * x.W * C * 2;
+    sa.box[0] = 64; sa.box[1] = tw; sa.box[2] = 1; sa.box[3] = th; sa.box[4] = tn;
+    p.tdim[0] = ceil_div(Wo, tw); p.tdim[1] = 1; p.tdim[2] = ceil_div(Ho, th); p.tdim[3] = ceil_div(x.N, tn);
+    p.box[0] = tw; p.box[1] = 1; p.box[2] = th; p.box[3] = tn;
+    p.ext[0] = Wo; p.ext[1] = 1; p.ext[2] = Ho; p.ext[3] = x.N;
+    p.a_mul[0] = tw; p.a_mul[1] = 0; p.a_mul[2] = th; p.a_mul[3] = tn;
+    const int padl = o.asym ? 0 : 1;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        const int t = ky * 3 + kx;
+        const int ex = kx - padl, ey = ky - padl;
+        const int px = ex & 1, py = ey & 1;
+        const int ox = (ex - px) / 2, oy = (ey - py) / 2;
+        p.tap_a[t][0] = px * x.C; p.tap_a[t][1] = ox; p.tap_a[t][2] = py; p.tap_a[t][3] = oy; p.tap_a[t][4] = 0;
+        p.tap_b[t][0] = 0; p.tap_b[t][1] = t; p.tap_b[t][2] = 0; p.tap_b[t][3] = 0;
+      }
+    p.ostride[0] = ldo; p.ostride[1] = 0; p.ostride[2] = static_cast<long long>(Wo) * ldo;
+    p.ostride[3] = static_cast<long long>(Ho) * Wo * ldo;
+    p.kchunks = x.C / 64;
+  }
+  fill_strides(sa);
+
+  sb.base = w.w;
+  sb.dim[0] = w.cin_pad; sb.dim[1] = w.rows; sb.dim[2] = taps; sb.dim[3] = 1; sb.dim[4] = 1;
+  sb.stride[0] = w.cin_pad * 2ull; sb.stride[1] = 2ull * w.rows * w.cin_pad; sb.stride[2] = 2ull * taps * w.rows * w.cin_pad;
+  sb.stride[3] = sb.stride[2];
+  fill_strides(sb);
+
+  const long long m_tiles = 1ll * p.tdim[0] * p.tdim[1] * p.tdim[2] * p.tdim[3];
+  p.N = gemm_n;
+  p.BN = pick_bn(m_tiles, gemm_n, false);
+  p.n_tiles = ceil_div(gemm_n, p.BN);
+  sb.box[0] = 64; sb.box[1] = p.BN; sb.box[2] = 1; sb.box[3] = 1; sb.box[4] = 1;
+  p.num_taps = taps;
+  p.idesc = make_idesc(dtype, p.BN);
+  p.ocol = 1;
+  p.out_fp32 = o.out_fp32 ? 1 : 0;
+  if (o.to_io_out_nchw) {
+    p.out = nullptr;                                   // patched from IO at launch
+    const long long hw = static_cast<long long>(Ho) * Wo;
+    p.ostride[0] = 1; p.ostride[1] = Wo; p.ostride[2] = hw * outc; p.ostride[3] = 0;
+    p.ocol = hw;
+  } else {
+    p.out = out.p;
+  }
+  if (o.res) {
+    I2IT_CHECK(o.stride == 1, "conv: residual only on stride-1 convs");
+    p.res = o.res->p;
+    const long long ldr = o.res->ld;
+    p.rstride[0] = ldr; p.rstride[1] = static_cast<long long>(Wo) * ldr; p.rstride[2] = static_cast<long long>(Ho) * Wo * ldr;
+    p.rcol = 1;
+  }
+  p.bias = w.bias;
+  p.bias_mode = (o.bias_mode >= 0) ? o.bias_mode : (w.bias ? TG_BIAS_COL : TG_BIAS_NONE);
+  if (!w.bias) p.bias_mode = TG_BIAS_NONE;
+  p.alpha = o.alpha;
+  p.act = o.act;
+  p.err = d_err;
+
+  const CUtensorMap ta = encode_tmap(sa, dtype), tb = encode_tmap(sb, dtype);
+  const int grid = static_cast<int>(std::min<long long>(m_tiles * p.n_tiles, num_sms));
+  launch_gemm(P, ta, tb, p, grid, o.to_io_out_nchw);
+  return out;
+}
+
+Act Engine::linear(Plan& P, const Act& x, const PW& w, const Act* res, int act) {
+  ConvOpts o;
+  o.ksize = 1;
+  o.act = act;
+  Act xr = x.as_rows(), rr;
+  if (res) { rr = res->as_rows(); o.res = &rr; }
+  Act y = conv(P, xr, w, o);
+  y.N = x.N; y.H = x.H; y.W = x.W;
+  return y;
+}
+
+Act Engine::group_norm(Plan& P, const Act& x, const NormW& nw, float eps, bool silu) {
+  I2IT_CHECK(x.C == nw.C && x.C % 32 == 0 && x.C % 8 == 0, "group_norm: bad channel count " + std::to_string(x.C));
+  const int C = x.C, HW = x.H * x.W, cg = C / 32, vecs = C / 8;
+  I2IT_CHECK(vecs <= 1024, "group_norm: too many channels");
+  const int rows = std::max(1, 256 / vecs), threads = vecs * rows;
+  const int chunks = std::max(1, std::min(256, ceil_div(HW, rows * 4)));
+  const int pix = ceil_div(HW, chunks);
+  auto partial = alloc_raw(P, static_cast<size_t>(x.N) * chunks * 64 * sizeof(float));
+  auto stats = alloc_raw(P, static_cast<size_t>(x.N) * 64 * sizeof(float));
+  Act y = alloc_act(P, x.N, x.H, x.W, C);
+  float* d_part = static_cast<float*>(partial.get());
+  float* d_stats = static_cast<float*>(stats.get());
+  const uint16_t* xp = x.p;
+  uint16_t* yp = y.p;
+  const long long ximg = x.img(), yimg = y.img();
+  const int ldx = x.ld, ldy = y.ld, N = x.N, dt = dtype, isilu = silu ? 1 : 0;
+  const float* g = nw.g;
+  const float* b = nw.b;
+  add_op(P, [=](cudaStream_t st) {
+    DISPATCH_T(dt, (gn_stats_kernel<T><<<dim3(chunks, N), threads, 2 * C * sizeof(float), st>>>(
+                       reinterpret_cast<const T*>(xp), ximg, ldx, C, HW, cg, pix, d_part)));
+  });
+  const double inv_count = 1.0 / (static_cast<double>(HW) * cg);
+  add_op(P, [=](cudaStream_t st) { gn_finalize_kernel<<<N, 32, 0, st>>>(d_part, chunks, inv_count, eps, d_stats); });
+  add_op(P, [=](cudaStream_t st) {
+    DISPATCH_T(dt, (gn_apply_kernel<T><<<dim3(chunks, N), threads, 0, st>>>(
+                       reinterpret_cast<const T*>(xp), ximg, ldx, reinterpret_cast<T*>(yp), yimg, ldy, C, HW, cg, pix,
+                       d_stats, g, b, isilu)));
+  });
+  return y;
+}
+
+Act Engine::layer_norm(Plan& P, const Act& x, const NormW& nw) {
+  I2IT_CHECK(x.C == nw.C && x.C % 8 == 0 && x.C <= 1280, "layer_norm: C must be a multiple of 8 and <= 1280");
+  Act y = alloc_act(P, x.N, x.H, x.W, x.C);
+  const long long rows = x.rows();
+  const uint16_t* xp = x.p;
+  uint16_t* yp = y.p;
+  const int ldx = x.ld, ldy = y.ld, C = x.C, dt = dtype;
+  const float* g = nw.g;
+  const float* b = nw.b;
+  add_op(P, [=](cudaStream_t st) {
+    DISPATCH_T(dt, (layernorm_kernel<T><<<ceil_div(rows * 32, 256), 256, 0, st>>>(
+                       reinterpret_cast<const T*>(xp), ldx, reinterpret_cast<T*>(yp), ldy, static_cast<int>(rows), C, g, b,
+                       1e-5f)));
+  });
+  return y;
+}
+
+Act Engine::upsample2x(Plan& P, const Act& x) {
+  Act y = alloc_act(P, x.N, 2 * x.H, 2 * x.W, x.C);
+  const long long total = static_cast<long long>(x.N) * 4 * x.H * x.W * (x.C / 8);
+  const uint16_t* xp = x.p;
+  uint16_t* yp = y.p;
+  const int ldx = x.ld, ldy = y.ld, H = x.H, W = x.W, C = x.C, dt = dtype;
+  add_op(P, [=](cudaStream_t st) {
+    DISPATCH_T(dt, (upsample2x_kernel<T><<<ceil_div(total, 256), 256, 0, st>>>(reinterpret_cast<const T*>(xp), ldx,
+                                                                             reinterpret_cast<T*>(yp), ldy, H, W, C, total)));
+  });
+  return y;
+}
+
+void Engine::copy_channels(Plan& P, const Act& src, const Act& dst) {
+  I2IT_CHECK(src.C == dst.C && src.rows() == dst.rows() && src.C % 8 == 0, "copy_channels: shape mismatch");
+  const long long total = src.rows() * (src.C / 8);
+  const uint16_t* xp = src.p;
+  uint16_t* yp = dst.p;
+  const int ldx = src.ld, ldy = dst.ld, C = src.C, dt = dtype;
+  add_op(P, [=](cudaStream_t st) {
+    DISPATCH_T(dt, (copy2d_kernel<T><<<ceil_div(total, 256), 256, 0, st>>>(reinterpret_cast<const T*>(xp), ldx,
+                                                                         reinterpret_cast<T*>(yp), ldy, C, total)));
+  });
+}
+
+Act Engine::vt_proj(Plan& P, const Act& x, int B, int ntok, const PW& wv) {
+  I2IT_CHECK(x.rows() == static_cast<long long>(B) * ntok, "vt_proj: token count mismatch");
+  I2IT_CHECK(x.C == wv.cin || x.C == wv.cin_pad, "vt_proj: width mismatch");
+  const int C = wv.rows, ldv = round_up(ntok, 8);
+  Act vt = alloc_act(P, B, 1, C, ldv, ldv);      // [B][C rows][ldv]; "C" field carries the padded token count
+  TmapSpec sa, sb;
+  TapGemmParams p;
+  std::memset(&p, 0, sizeof p);
+  sa.base = wv.w;
+  sa.dim[0] = wv.cin_pad; sa.dim[1] = C;
+  sa.stride[0] = wv.cin_pad * 2ull; sa.stride[1] = 2ull * C * wv.cin_pad; sa.stride[2] = sa.stride[1]; sa.stride[3] = sa.stride[1];
+  sa.box[0] = 64; sa.box[1] = 128;
+  fill_strides(sa);
+  sb.base = x.p;
+  sb.dim[0] = x.C; sb.dim[1] = ntok; sb.dim[2] = 1; sb.dim[3] = B; sb.dim[4] = 1;
+  sb.stride[0] = x.ld * 2ull; sb.stride[1] = 2ull * ntok * x.ld; sb.stride[2] = 2ull * ntok * x.ld; sb.stride[3] = sb.stride[2];
+  fill_strides(sb);
+  p.tdim[0] = ceil_div(C, 128); p.tdim[1] = 1; p.tdim[2] = B; p.tdim[3] = 1;
+  p.box[0] = 128; p.box[1] = 1; p.box[2] = 1; p.box[3] = 1;
+  p.ext[0] = C; p.ext[1] = 1; p.ext[2] = B; p.ext[3] = 1;
+  p.a_mul[0] = 128;
+  p.b_mul[0] = 0; p.b_mul[1] = 1; p.b_mul[2] = 0;
+  const long long m_tiles = 1ll * p.tdim[0] * B;
+  p.N = ntok;
+  p.BN = pick_bn(m_tiles, ntok, false);
+  p.n_tiles = ceil_div(ntok, p.BN);
+  sb.box[0] = 64; sb.box[1] = p.BN;
+  p.num_taps = 1;
+  p.kchunks = ceil_div(x.C, 64);
+  p.idesc = make_idesc(dtype, p.BN);
+  p.out = vt.p;
+  p.ostride[0] = ldv; p.ostride[1] = 0; p.ostride[2] = static_cast<long long>(C) * ldv; p.ostride[3] = 0;
+  p.ocol = 1;
+  p.bias = wv.bias;
+  p.bias_mode = wv.bias ? TG_BIAS_ROW : TG_BIAS_NONE;
+  p.alpha = 1.f;
+  p.err = d_err;
+  const CUtensorMap ta = encode_tmap(sa, dtype), tb = encode_tmap(sb, dtype);
+  launch_gemm(P, ta, tb, p, static_cast<int>(std::min<long long>(m_tiles * p.n_tiles, num_sms)), false);
+  return vt;
+}
+
+Act Engine::attention(Plan& P, const Act& q, const Act& k, const Act& vt, int B, int Nq, int Nk, int heads, int d,
+                      int kv_batch) {
+  I2IT_CHECK(d % 64 == 0 && (d <= 256 || d % 256 == 0), "attention: head dim must be a multiple of 64");
+  I2IT_CHECK(Nk <= 4096, "attention: Nk > 4096 needs the fused kernel");
+  I2IT_CHECK(kv_batch == B || kv_batch == 1, "attention: kv batch must be 1 or B");
+  const int C = heads * d, lds = round_up(Nk, 8);
+  const long long rows = static_cast<long long>(B) * heads * Nq;
+  auto sbuf = alloc_raw(P, static_cast<size_t>(rows) * lds * sizeof(float));
+  auto pbuf = alloc_raw(P, static_cast<size_t>(rows) * lds * 2);
+  float* S = static_cast<float*>(sbuf.get());
+  uint16_t* Pm = static_cast<uint16_t*>(pbuf.get());
+  Act out = alloc_act(P, B, 1, Nq, C);
+  const int kvb = (kv_batch == B) ? 1 : 0;
+
+  {  // S = alpha * Q K^T   (fp32 logits)
+    TmapSpec sa, sb;
+    TapGemmParams p;
+    std::memset(&p, 0, sizeof p);
+    sa.base = q.p;
+    sa.dim[0] = d; sa.dim[1] = Nq; sa.dim[2] = heads; sa.dim[3] = B;
+    sa.stride[0] = q.ld * 2ull; sa.stride[1] = d * 2ull; sa.stride[2] = 2ull * Nq * q.ld; sa.stride[3] = sa.stride[2];
+    sa.box[0] = 64; sa.box[1] = 128;
+    fill_strides(sa);
+    sb.base = k.p;
+    sb.dim[0] = d; sb.dim[1] = Nk; sb.dim[2] = heads; sb.dim[3] = kv_batch;
+    sb.stride[0] = k.ld * 2ull; sb.stride[1] = d * 2ull; sb.stride[2] = 2ull * Nk * k.ld; sb.stride[3] = sb.stride[2];
+    fill_strides(sb);
+    p.tdim[0] = ceil_div(Nq, 128); p.tdim[1] = heads; p.tdim[2] = B; p.tdim[3] = 1;
+    p.box[0] = 128; p.box[1] = 1; p.box[2] = 1; p.box[3] = 1;
+    p.ext[0] = Nq; p.ext[1] = heads; p.ext[2] = B; p.ext[3] = 1;
+    p.a_mul[0] = 128; p.a_mul[1] = 1; p.a_mul[2] = 1;
+    p.b_mul[0] = 1; p.b_mul[1] = kvb; p.b_mul[2] = 0;
+    const long long m_tiles = 1ll * p.tdim[0] * heads * B;
+    p.N = Nk;
+    p.BN = pick_bn(m_tiles, Nk, false);
+    p.n_tiles = ceil_div(Nk, p.BN);
+    sb.box[0] = 64; sb.box[1] = p.BN;
+    p.num_taps = 1;
+    p.kchunks = d / 64;
+    p.idesc = make_idesc(dtype, p.BN);
+    p.out = S;
+    p.out_fp32 = 1;
+    p.ostride[0] = lds; p.ostride[1] = static_cast<long long>(Nq) * lds; p.ostride[2] = static_cast<long long>(heads) * Nq * lds;
+    p.ocol = 1;
+    p.alpha = 1.0f / sqrtf(static_cast<float>(d));
+    p.err = d_err;
+    const CUtensorMap ta = encode_tmap(sa, dtype), tb = encode_tmap(sb, dtype);
+    launch_gemm(P, ta, tb, p, static_cast<int>(std::min<long long>(m_tiles * p.n_tiles, num_sms)), false);
+  }
+  {  // P = softmax(S)
+    const int dt = dtype;
+    if (Nk > 1024) {
+      add_op(P, [=](cudaStream_t st) {
+        DISPATCH_T(dt, (softmax_kernel<T, 128><<<static_cast<unsigned>(rows), 128, 0, st>>>(S, lds, reinterpret_cast<T*>(Pm), lds,
+                                                                                          rows, Nk, lds)));
+      });
+    } else {
+      add_op(P, [=](cudaStream_t st) {
+        DISPATCH_T(dt, (softmax_kernel<T, 32><<<static_cast<unsigned>((rows + 3) / 4), 128, 0, st>>>(
+                           S, lds, reinterpret_cast<T*>(Pm), lds, rows, Nk, lds)));
+      });
+    }
+  }
+  {  // O = P V   (V given transposed: [kvB][C][ldv])
+    TmapSpec sa, sb;
+    TapGemmParams p;
+    std::memset(&p, 0, sizeof p);
+    sa.base = Pm;
+    sa.dim[0] = Nk; sa.dim[1] = Nq; sa.dim[2] = heads; sa.dim[3] = B;
+    sa.stride[0] = lds * 2ull; sa.stride[1] = 2ull * Nq * lds; sa.stride[2] = 2ull * heads * Nq * lds; sa.stride[3] = sa.stride[2];
+    sa.box[0] = 64; sa.box[1] = 128;
+    fill_strides(sa);
+    const int ldv = vt.ld;
+    sb.base = vt.p;
+    sb.dim[0] = Nk; sb.dim[1] = d; sb.dim[2] = heads; sb.dim[3] = kv_batch;
+    sb.stride[0] = ldv * 2ull; sb.stride[1] = 2ull * d * ldv; sb.stride[2] = 2ull * C * ldv; sb.stride[3] = sb.stride[2];
+    fill_strides(sb);
+    p.tdim[0] = ceil_div(Nq, 128); p.tdim[1] = heads; p.tdim[2] = B; p.tdim[3] = 1;
+    p.box[0] = 128; p.box[1] = 1; p.box[2] = 1; p.box[3] = 1;
+    p.ext[0] = Nq; p.ext[1] = heads; p.ext[2] = B; p.ext[3] = 1;
+    p.a_mul[0] = 128; p.a_mul[1] = 1; p.a_mul[2] = 1;
+    p.b_mul[0] = 1; p.b_mul[1] = kvb; p.b_mul[2] = 0;
+    const long long m_tiles = 1ll * p.tdim[0] * heads * B;
+    p.N = d;
+    p.BN = std::min(d, 256);
+    p.n_tiles = ceil_div(d, p.BN);
+    sb.box[0] = 64; sb.box[1] = p.BN;
+    p.num_taps = 1;
+    p.kchunks = ceil_div(Nk, 64);
+    p.idesc = make_idesc(dtype, p.BN);
+    p.out = out.p;
+    p.ostride[0] = out.ld; p.ostride[1] = d; p.ostride[2] = static_cast<long long>(Nq) * out.ld;
+    p.ocol = 1;
+    p.alpha = 1.f;
+    p.err = d_err;
+    const CUtensorMap ta = encode_tmap(sa, dtype), tb = encode_tmap(sb, dtype);
+    launch_gemm(P, ta, tb, p, static_cast<int>(std::min<long long>(m_tiles * p.n_tiles, num_sms)), false);
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// executor
+// ---------------------------------------------------------------------------------------------
+void Engine::forward(const IO& io, int B, int H, int W, int direction, int text_batch, cudaStream_t st) {
+  I2IT_CHECK(H % 64 == 0 && W % 64 == 0 && H > 0 && W > 0, "H and W must be positive multiples of 64");
+  I2IT_CHECK(B > 0 && (text_batch == 1 || text_batch == B), "text_batch must be 1 or batch");
+  I2IT_CHECK(io.x && io.text && io.eps && io.out, "null input/output pointer");
+  Plan* P = plan_for(B, H, W, direction, text_batch);
+  P->io = io;
+  last_plan_ = P;
+  if (cfg.use_cuda_graph) {
+    if (!(P->gexec && P->gio == io)) {
+      if (P->gexec) { cudaGraphExecDestroy(P->gexec); P->gexec = nullptr; }
+      cudaGraph_t g = nullptr;
+      I2IT_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      for (auto& op : P->ops) op(st);
+      I2IT_CUDA(cudaStreamEndCapture(st, &g));
+      I2IT_CUDA(cudaGraphInstantiate(&P->gexec, g, 0));
+      cudaGraphDestroy(g);
+      P->gio = io;
+    }
+    I2IT_CUDA(cudaGraphLaunch(P->gexec, st));
+  } else {
+    for (auto& op : P->ops) op(st);
+    I2IT_CUDA(cudaGetLastError());
+  }
+}
+
+__global__ void stage_to_nchw_f32_kernel(const uint16_t* x, int ld, int C, long long HW, long long total, float* out,
+                                         int is_bf16) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // over N*C*HW (NCHW order)
+  if (i >= total) return;
+  const long long p = i % HW;
+  const long long r = i / HW;
+  const int c = static_cast<int>(r % C);
+  const long long n = r / C;
+  const uint16_t v = x[(n * HW + p) * ld + c];
+  out[i] = is_bf16 ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&v))
+                   : __half2float(*reinterpret_cast<const __half*>(&v));
+}
+
+void Engine::read_stage(const std::string& name, float* dst, size_t dst_elems, int dims[4]) {
+  I2IT_CHECK(last_plan_ != nullptr, "no forward has run yet");
+  auto it = last_plan_->stages.find(name);
+  I2IT_CHECK(it != last_plan_->stages.end(), "unknown stage '" + name + "' (was keep_stages set?)");
+  const Act& a = it->second;
+  dims[0] = a.N; dims[1] = a.C; dims[2] = a.H; dims[3] = a.W;
+  const long long HW = static_cast<long long>(a.H) * a.W, total = HW * a.C * a.N;
+  I2IT_CHECK(static_cast<size_t>(total) <= dst_elems, "read_stage: destination too small");
+  I2IT_CUDA(cudaDeviceSynchronize());
+  stage_to_nchw_f32_kernel<<<ceil_div(total, 256), 256>>>(a.p, a.ld, a.C, HW, total, dst, dtype == DT_BF16);
+  I2IT_CUDA(cudaDeviceSynchronize());
+}
+
+}  // namespace i2it

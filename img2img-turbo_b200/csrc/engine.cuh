@@ -1,0 +1,172 @@
+// Engine: weight store, load-time fold, plan builder (the model graph) and executor behind the C ABI.
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/i2it.h"
+#include "kernels.cuh"
+#include "tapgemm.cuh"
+
+namespace i2it {
+
+// ---------------------------------------------------------------------------------------------
+// TMA tensor-map encoding (driver entry point fetched through the runtime: no libcuda link dependency)
+// ---------------------------------------------------------------------------------------------
+struct TmapSpec {
+  const void* base = nullptr;
+  uint64_t dim[5] = {1, 1, 1, 1, 1};
+  uint64_t stride[4] = {16, 16, 16, 16};   // bytes, dims 1..4
+  uint32_t box[5] = {1, 1, 1, 1, 1};
+};
+CUtensorMap encode_tmap(const TmapSpec& s, int dtype);
+
+// ---------------------------------------------------------------------------------------------
+// workspace pool (plan-build time only; execution never allocates)
+// ---------------------------------------------------------------------------------------------
+struct Pool {
+  std::vector<std::pair<void*, size_t>> blocks;
+  std::multimap<size_t, void*> free_;
+  size_t total = 0;
+  ~Pool();
+  void* get(size_t bytes, size_t* actual);
+  void put(void* p, size_t bytes) { free_.emplace(bytes, p); }
+};
+
+struct Act {                       // NHWC view, 2-byte elements
+  std::shared_ptr<void> hold;
+  uint16_t* p = nullptr;
+  int N = 0, H = 0, W = 0, C = 0, ld = 0;
+  long long img() const { return static_cast<long long>(H) * W * ld; }
+  long long rows() const { return static_cast<long long>(N) * H * W; }
+  Act as_rows() const { Act a = *this; a.W = static_cast<int>(rows()); a.N = 1; a.H = 1; return a; }
+  Act slice(int c0, int c) const { Act a = *this; a.p = p + c0; a.C = c; return a; }
+};
+
+struct PW {                        // prepared (folded, re-laid-out) weight: [taps][rows][cin_pad] + fp32 bias
+  uint16_t* w = nullptr;
+  float* bias = nullptr;
+  int rows = 0, cin = 0, cin_pad = 0, taps = 1;
+};
+struct NormW { const float* g = nullptr; const float* b = nullptr; int C = 0; };
+
+struct IO {
+  const void* x = nullptr; const void* text = nullptr; const void* eps = nullptr; const void* noise = nullptr;
+  float r = 1.f; void* out = nullptr; void* out_latent = nullptr;
+  bool operator==(const IO& o) const { return std::memcmp(this, &o, sizeof(IO)) == 0; }
+};
+
+struct Plan {
+  Pool pool;                                           // declared first: destroyed last
+  std::vector<std::function<void(cudaStream_t)>> ops;  // one kernel launch each
+  std::map<std::string, Act> stages;
+  std::vector<std::shared_ptr<void>> keep;
+  IO io;
+  cudaGraphExec_t gexec = nullptr;
+  IO gio;
+  ~Plan() { if (gexec) cudaGraphExecDestroy(gexec); }
+};
+
+struct ConvOpts {
+  int ksize = 3, stride = 1;
+  bool asym = false;             // VAE Downsample2D: F.pad(0,1,0,1) then pad-0 stride-2 conv
+  const Act* res = nullptr;
+  int act = TG_ACT_NONE;
+  const Act* out = nullptr;      // write into this view instead of allocating
+  bool out_fp32 = false;
+  float alpha = 1.f;
+  bool to_io_out_nchw = false;   // final image: write NCHW straight into IO.out
+  int bias_mode = -1;            // -1: column bias iff the weight has one
+};
+
+struct WT {                      // raw fp32 tensor of the state dict, on device
+  float* d = nullptr;
+  std::vector<int64_t> shape;
+  long long numel = 0;
+};
+
+class Engine {
+ public:
+  explicit Engine(const i2it_config& c);
+  ~Engine();
+  i2it_config cfg;
+  int dtype, num_sms;
+  std::string last_error;
+
+  void set_weight(const std::string& key, const void* data, const int64_t* shape, int ndim, int dt, bool is_dev);
+  void set_adapter_scale(const std::string& a, float s) { adapter_scale_[a] = s; }
+  void finalize(float lw_unet, float lw_vae, float skip_gamma, float twin_r);
+  Plan* plan_for(int B, int H, int W, int direction, int text_batch);
+  void forward(const IO& io, int B, int H, int W, int direction, int text_batch, cudaStream_t st);
+  void read_stage(const std::string& name, float* dst, size_t dst_elems, int dims[4]);
+
+  // ---- op builders (append launches to a plan) ----
+  Act alloc_act(Plan& P, int N, int H, int W, int C, int ld = 0, bool zero_persistent = false);
+  std::shared_ptr<void> alloc_raw(Plan& P, size_t bytes);
+  Act conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o);
+  Act linear(Plan& P, const Act& x, const PW& w, const Act* res = nullptr, int act = TG_ACT_NONE);
+  Act group_norm(Plan& P, const Act& x, const NormW& nw, float eps, bool silu);
+  Act layer_norm(Plan& P, const Act& x, const NormW& nw);
+  Act upsample2x(Plan& P, const Act& x);
+  void copy_channels(Plan& P, const Act& src, const Act& dst_slice);
+  // V^T[b] = Wv X[b]^T (+ row bias): returns [B][C][ldv] as an Act with N=B,H=1,W=C,ld=ldv (C field = Ntok)
+  Act vt_proj(Plan& P, const Act& x_tokens, int B, int ntok, const PW& wv);
+  // attention core on projected operands; q/k are column slices of token matrices; returns [B*Nq, heads*d]
+  Act attention(Plan& P, const Act& q, const Act& k, const Act& vt, int B, int Nq, int Nk, int heads, int d,
+                int kv_batch);
+
+  // ---- weights ----
+  bool has(const std::string& key) const;
+  const WT& raw(const std::string& name, const char* what) const;   // accepts X.what or X.base_layer.what
+  PW prep(const std::string& cache_key, const std::vector<std::string>& names, bool geglu = false,
+          float scale = 1.f, const float* bias_add = nullptr);
+  PW prep_twin(const std::string& pre, const std::string& cur, float r);
+  NormW norm(const std::string& name);
+  const float* temb_bias(const std::string& resnet_prefix);          // time_emb_proj(silu(emb)) at t=999
+  void free_prepared();
+
+  // ---- model graph ----
+  Act build_vae_encoder(Plan& P, const std::string& vp, int B, int H, int W, std::vector<Act>& skips);
+  Act build_unet(Plan& P, const Act& z, int text_batch);
+  void build_vae_decoder(Plan& P, const std::string& vp, const Act& dec_in, std::vector<Act>& skips);
+  Act vae_resnet(Plan& P, const std::string& p, const Act& x);
+  Act vae_attn(Plan& P, const std::string& p, const Act& x);
+  Act unet_resnet(Plan& P, const std::string& p, const Act& x);
+  Act unet_xformer(Plan& P, const std::string& p, const Act& x, int heads, int text_batch);
+  void mark(Plan& P, const std::string& name, const Act& a) { if (cfg.keep_stages) P.stages[name] = a; }
+
+  template <typename F> void add_op(Plan& P, F&& f) { P.ops.emplace_back(std::forward<F>(f)); }
+  void launch_gemm(Plan& P, const CUtensorMap& ta, const CUtensorMap& tb, const TapGemmParams& p, int grid,
+                   bool out_from_io);
+  int pick_bn(long long m_tiles, int N, bool even32) const;
+
+  int* d_err = nullptr;      // device alias of a mapped host word written by the tapgemm watchdog
+  int* err_host_ = nullptr;
+  void check_device_error();
+
+ private:
+  std::unordered_map<std::string, WT> w_;
+  std::unordered_map<std::string, float> adapter_scale_;
+  float lw_unet_ = 1.f, lw_vae_ = 1.f, skip_gamma_ = 1.f, twin_r_ = -1.f;
+  bool finalized_ = false;
+  std::unordered_map<std::string, PW> prepared_;
+  std::unordered_map<std::string, float*> prepared_f32_;
+  std::vector<void*> prep_allocs_;
+  float* scratch_ = nullptr; long long scratch_n_ = 0;
+  float* emb_act_ = nullptr;
+  std::map<std::vector<int>, std::unique_ptr<Plan>> plans_;
+  Plan* last_plan_ = nullptr;
+  Act text_;                     // staged text embedding while a UNet plan is being built
+
+  float* fold_f32(const std::string& name, long long* numel, float c0 = 1.f, const std::string& other = "",
+                  float c1 = 0.f);
+  float adapter_weight(const std::string& name, const std::string& adapter) const;
+  void* dmalloc(size_t bytes);
+};
+
+}  // namespace i2it

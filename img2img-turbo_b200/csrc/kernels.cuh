@@ -1,0 +1,362 @@
+// HBM-bound kernels of the path: GroupNorm(+SiLU), LayerNorm, softmax, layout / latent elementwise ops,
+// and the load-time weight preparation (LoRA fold, TwinConv blend, re-layout, time-embedding constants).
+// All activations are NHWC with an explicit pixel stride `ld` (elements) so channel slices are addressable.
+#pragma once
+#include "common.cuh"
+
+namespace i2it {
+
+// =============================================================================================
+// GroupNorm (+SiLU)   — replaces ATen group_norm + silu at every norm1/norm2/conv_norm_out/
+// Transformer2DModel.norm/attn.group_norm under the reference's vae.encode/unet/vae.decode calls
+// (/root/reference/src/pix2pix_turbo.py:198-203).  Three launches: partial sums (deterministic,
+// no atomics to global), finalize (double), apply.  Algorithmic bytes: 2 reads + 1 write of the tensor.
+// =============================================================================================
+template <typename T>
+__global__ void gn_stats_kernel(const T* __restrict__ x, long long img_stride, int ld, int C, int HW, int cg,
+                                int pix_per_cta, float* __restrict__ partial /*[N][chunks][32][2]*/) {
+  extern __shared__ float s_acc[];   // [2*C]
+  const int vecs = C >> 3;
+  const int vx = threadIdx.x % vecs, vy = threadIdx.x / vecs, rows = blockDim.x / vecs;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  const int p0 = chunk * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+  const T* xb = x + n * img_stride + vx * 8;
+  if (vy < rows) {
+    for (int p = p0 + vy; p < p1; p += rows) {
+      const uint4 u = ld_nc16(xb + static_cast<long long>(p) * ld);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = Elem<T>::unpack(w[i]);
+        s[2 * i] += f.x; q[2 * i] += f.x * f.x;
+        s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&s_acc[vx * 8 + i], s[i]);
+      atomicAdd(&s_acc[C + vx * 8 + i], q[i]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int g = threadIdx.x;
+    float a = 0.f, b = 0.f;
+    for (int c = g * cg; c < (g + 1) * cg; ++c) { a += s_acc[c]; b += s_acc[C + c]; }
+    float* o = partial + ((static_cast<long long>(n) * gridDim.x + chunk) * 32 + g) * 2;
+    o[0] = a; o[1] = b;
+  }
+}
+
+static __global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, double inv_count, float eps,
+                                   float* __restrict__ stats /*[N][32][2] = mean, rstd*/) {
+  const int n = blockIdx.x, g = threadIdx.x;
+  double a = 0.0, b = 0.0;
+  for (int c = 0; c < chunks; ++c) {
+    const float* o = partial + ((static_cast<long long>(n) * chunks + c) * 32 + g) * 2;
+    a += o[0]; b += o[1];
+  }
+  const double mean = a * inv_count;
+  double var = b * inv_count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  stats[(n * 32 + g) * 2] = static_cast<float>(mean);
+  stats[(n * 32 + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+template <typename T>
+__global__ void gn_apply_kernel(const T* __restrict__ x, long long ximg, int ldx, T* __restrict__ y, long long yimg,
+                                int ldy, int C, int HW, int cg, int pix_per_cta, const float* __restrict__ stats,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu) {
+  const int vecs = C >> 3;
+  const int vx = threadIdx.x % vecs, vy = threadIdx.x / vecs, rows = blockDim.x / vecs;
+  const int n = blockIdx.y;
+  if (vy >= rows) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = vx * 8 + i, g = c / cg;
+    const float mean = stats[(n * 32 + g) * 2], rstd = stats[(n * 32 + g) * 2 + 1];
+    sc[i] = rstd * gamma[c];
+    sh[i] = beta[c] - mean * sc[i];
+  }
+  const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+  const T* xb = x + n * ximg + vx * 8;
+  T* yb = y + n * yimg + vx * 8;
+  for (int p = p0 + vy; p < p1; p += rows) {
+    const uint4 u = ld_nc16(xb + static_cast<long long>(p) * ldx);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = Elem<T>::unpack(w[i]);
+      float a = f.x * sc[2 * i] + sh[2 * i], b = f.y * sc[2 * i + 1] + sh[2 * i + 1];
+      if (silu) { a = silu_f(a); b = silu_f(b); }
+      o[i] = Elem<T>::pack(a, b);
+    }
+    st16(yb + static_cast<long long>(p) * ldy, make_uint4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// =============================================================================================
+// LayerNorm over the channel dim of token rows (BasicTransformerBlock.norm1/2/3), one warp per row.
+// =============================================================================================
+template <typename T>
+__global__ void layernorm_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int rows, int C,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+  constexpr int MAXV = 5;   // C <= 1280
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int vecs = C >> 3;
+  float v[MAXV][8];
+  float sum = 0.f;
+  const T* xr = x + static_cast<long long>(warp) * ldx;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = lane + 32 * k;
+    if (vi < vecs) {
+      const uint4 u = ld_nc16(xr + vi * 8);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = Elem<T>::unpack(w[i]);
+        v[k][2 * i] = f.x; v[k][2 * i + 1] = f.y;
+        sum += f.x + f.y;
+      }
+    }
+  }
+  const float mean = warp_sum(sum) / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    if (lane + 32 * k < vecs) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = v[k][i] - mean; sq += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / C + eps);
+  T* yr = y + static_cast<long long>(warp) * ldy;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = lane + 32 * k;
+    if (vi < vecs) {
+      uint32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = vi * 8 + 2 * i;
+        o[i] = Elem<T>::pack((v[k][2 * i] - mean) * rstd * gamma[c] + beta[c],
+                             (v[k][2 * i + 1] - mean) * rstd * gamma[c + 1] + beta[c + 1]);
+      }
+      st16(yr + vi * 8, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+  }
+}
+
+// =============================================================================================
+// Row softmax: fp32 logits (already scaled) -> probabilities in the activation dtype.
+// TPR threads cooperate on one row (32 or 128); up to 32 values per thread live in registers.
+// =============================================================================================
+template <typename T, int TPR>
+__global__ void softmax_kernel(const float* __restrict__ s, long long lds, T* __restrict__ pr, long long ldp,
+                               long long rows, int nk, int nk_pad) {
+  constexpr int RPB = 128 / TPR;
+  const long long row = static_cast<long long>(blockIdx.x) * RPB + threadIdx.x / TPR;
+  const int tr = threadIdx.x % TPR;
+  __shared__ float red[4];
+  const bool ok = row < rows;
+  const float* sr = s + (ok ? row : 0) * lds;
+  float v[32];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = tr + i * TPR;
+    v[i] = (ok && c < nk) ? sr[c] : -INFINITY;
+    m = fmaxf(m, v[i]);
+  }
+  m = warp_max(m);
+  if (TPR == 128) {
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = tr + i * TPR;
+    v[i] = (c < nk) ? __expf(v[i] - m) : 0.f;
+    sum += v[i];
+  }
+  sum = warp_sum(sum);
+  if (TPR == 128) {
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    sum = red[0] + red[1] + red[2] + red[3];
+  }
+  if (!ok) return;
+  const float inv = 1.0f / sum;
+  T* o = pr + row * ldp;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = tr + i * TPR;
+    if (c < nk_pad) o[c] = Elem<T>::from_f(c < nk ? v[i] * inv : 0.f);
+  }
+}
+
+// =============================================================================================
+// boundary + latent elementwise kernels
+// =============================================================================================
+// NCHW [B,3,H,W] (act dtype) -> NHWC8 (channels 3..7 zero): the 3-channel boundary of vae.encode.
+template <typename T>
+__global__ void pack_input_kernel(const T* __restrict__ x, T* __restrict__ y, int C, long long HW, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // over B*HW pixels
+  if (i >= total) return;
+  const long long n = i / HW, p = i % HW;
+  uint32_t o[4] = {0, 0, 0, 0};
+  float c[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) c[k] = (k < C) ? Elem<T>::to_f(x[(n * C + k) * HW + p]) : 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o[k] = Elem<T>::pack(c[2 * k], c[2 * k + 1]);
+  st16(y + i * 8, make_uint4(o[0], o[1], o[2], o[3]));
+}
+
+// DiagonalGaussianDistribution.sample() * scaling_factor (+ the stochastic blend of
+// /root/reference/src/pix2pix_turbo.py:210): moments NHWC (ld) -> latent NHWC8 (channels 4..7 zero).
+template <typename T>
+__global__ void latent_sample_kernel(const T* __restrict__ mom, int ldm, const T* __restrict__ eps_nchw,
+                                     const T* __restrict__ noise_nchw, float r, float sf, T* __restrict__ z,
+                                     long long HW, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long n = i / HW, p = i % HW;
+  float o[8];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float mean = Elem<T>::to_f(mom[i * ldm + c]);
+    const float logvar = fminf(fmaxf(Elem<T>::to_f(mom[i * ldm + 4 + c]), -30.f), 20.f);
+    const float e = Elem<T>::to_f(eps_nchw[(n * 4 + c) * HW + p]);
+    float v = (mean + expf(0.5f * logvar) * e) * sf;
+    if (noise_nchw) {
+      // reference rounds the encoded latent to the activation dtype before blending
+      v = Elem<T>::to_f(Elem<T>::from_f(v)) * r + Elem<T>::to_f(noise_nchw[(n * 4 + c) * HW + p]) * (1.f - r);
+    }
+    o[c] = v;
+  }
+#pragma unroll
+  for (int c = 4; c < 8; ++c) o[c] = 0.f;
+  st16(z + i * 8, make_uint4(Elem<T>::pack(o[0], o[1]), Elem<T>::pack(o[2], o[3]), 0u, 0u));
+}
+
+// DDPMScheduler.step closed form at t=999 and the `/ scaling_factor` feeding vae.decode
+// (/root/reference/src/pix2pix_turbo.py:200-203): x0 = (x - s1*eps_hat)/sa, fp32 math, one rounding.
+template <typename T>
+__global__ void ddpm_step_kernel(const T* __restrict__ zin /*NHWC8*/, const T* __restrict__ pred, int ldp,
+                                 float s1, float sa, float inv_sf, T* __restrict__ dec_in /*NHWC8*/,
+                                 T* __restrict__ x0_nchw /*nullable*/, long long HW, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long n = i / HW, p = i % HW;
+  float o[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float x0 = (Elem<T>::to_f(zin[i * 8 + c]) - s1 * Elem<T>::to_f(pred[i * ldp + c])) / sa;
+    const float x0r = Elem<T>::to_f(Elem<T>::from_f(x0));        // x_denoised.to(dtype)
+    if (x0_nchw) x0_nchw[(n * 4 + c) * HW + p] = Elem<T>::from_f(x0);
+    o[c] = x0r * inv_sf;
+  }
+  st16(dec_in + i * 8, make_uint4(Elem<T>::pack(o[0], o[1]), Elem<T>::pack(o[2], o[3]), 0u, 0u));
+}
+
+// nearest 2x upsample, NHWC, 16-byte vectors
+template <typename T>
+__global__ void upsample2x_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int H, int W, int C,
+                                  long long total /* B*2H*2W*(C/8) */) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int vecs = C >> 3;
+  const int v = static_cast<int>(i % vecs);
+  long long p = i / vecs;
+  const int ox = static_cast<int>(p % (2 * W)); p /= (2 * W);
+  const int oy = static_cast<int>(p % (2 * H));
+  const long long n = p / (2 * H);
+  const uint4 u = ld_nc16(x + ((n * H + (oy >> 1)) * W + (ox >> 1)) * ldx + v * 8);
+  st16(y + ((n * 2 * H + oy) * 2 * W + ox) * ldy + v * 8, u);
+}
+
+// strided 2-D copy of 16-byte vectors: rows x (C/8) vectors (torch.cat along channels)
+template <typename T>
+__global__ void copy2d_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int C, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int vecs = C >> 3;
+  const long long r = i / vecs;
+  const int v = static_cast<int>(i % vecs);
+  st16(y + r * ldy + v * 8, ld_nc16(x + r * ldx + v * 8));
+}
+
+// =============================================================================================
+// load-time weight preparation (fp32 math, one rounding) — replaces ~1000 runtime peft LoRA kernels
+// =============================================================================================
+// acc[i] = c0*w0[i] (+ c1*w1[i])        (TwinConv blend: /root/reference/src/pix2pix_turbo.py:23-26)
+static __global__ void wprep_init_kernel(float* __restrict__ acc, const float* __restrict__ w0, float c0,
+                                  const float* __restrict__ w1, float c1, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) acc[i] = c0 * w0[i] + (w1 ? c1 * w1[i] : 0.f);
+}
+// acc[o][j] += s * sum_r B[o][r] * A[r][j]   (peft get_delta_weight for Linear and Conv2d; j = flattened cin*kh*kw)
+static __global__ void wprep_lora_kernel(float* __restrict__ acc, const float* __restrict__ A, const float* __restrict__ Bm,
+                                  float s, int rank, long long inner, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long o = i / inner, j = i % inner;
+  float d = 0.f;
+  for (int r = 0; r < rank; ++r) d += Bm[o * rank + r] * A[r * inner + j];
+  acc[i] += s * d;
+}
+// acc [Cout][Cin][taps] fp32 -> out[tap][row_map(o)][cin_pad] in T (zero padded); row_map handles the GEGLU
+// interleave and the row offset of fused projections.
+template <typename T>
+__global__ void wprep_store_kernel(const float* __restrict__ acc, T* __restrict__ out, int cout, int cin, int taps,
+                                   int cin_pad, int rows_total, int row_off, int interleave_half, float scale,
+                                   long long n /* cout*cin_pad*taps */) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int ci = static_cast<int>(i % cin_pad);
+  long long r = i / cin_pad;
+  const int o = static_cast<int>(r % cout);
+  const int t = static_cast<int>(r / cout);
+  int orow = o;
+  if (interleave_half > 0) orow = (o < interleave_half) ? 2 * o : 2 * (o - interleave_half) + 1;
+  orow += row_off;
+  const float v = (ci < cin) ? acc[(static_cast<long long>(o) * cin + ci) * taps + t] * scale : 0.f;
+  out[(static_cast<long long>(t) * rows_total + orow) * cin_pad + ci] = Elem<T>::from_f(v);
+}
+static __global__ void bias_store_kernel(const float* __restrict__ b, float* __restrict__ out, int cout, int row_off,
+                                  int interleave_half, const float* __restrict__ add) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= cout) return;
+  int orow = o;
+  if (interleave_half > 0) orow = (o < interleave_half) ? 2 * o : 2 * (o - interleave_half) + 1;
+  out[orow + row_off] = (b ? b[o] : 0.f) + (add ? add[o] : 0.f);
+}
+// y = act(W x + b), W [out][in] fp32, one warp per output (time-embedding MLP, computed once: t == 999)
+static __global__ void gemv_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ x,
+                            float* __restrict__ y, int out, int in, int silu_out) {
+  const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (o >= out) return;
+  float a = 0.f;
+  for (int i = lane; i < in; i += 32) a += W[static_cast<long long>(o) * in + i] * x[i];
+  a = warp_sum(a);
+  if (lane == 0) {
+    a += b ? b[o] : 0.f;
+    y[o] = silu_out ? silu_f(a) : a;
+  }
+}
+// acc[o][j] (Linear weight, fp32) fold helper for gemv inputs: reuse wprep_init/wprep_lora on a scratch copy.
+
+}  // namespace i2it

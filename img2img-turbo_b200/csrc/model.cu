@@ -1,0 +1,278 @@
+// The model graph of the hot path, appended op by op to a Plan (static shapes => one CUDA graph).
+//
+// Mirrors, layer for layer, what the reference executes through diffusers 0.25.1:
+//   VAE encoder  : my_vae_encoder_fwd        /root/reference/src/model.py:14-27   (+ quant_conv, posterior sample)
+//   UNet         : UNet2DConditionModel call /root/reference/src/pix2pix_turbo.py:199 (SD-Turbo config, t == 999)
+//   DDPM step    : sched.step                /root/reference/src/pix2pix_turbo.py:200 (closed form)
+//   VAE decoder  : my_vae_decoder_fwd        /root/reference/src/model.py:30-54   (skip convs, gamma)
+// with LoRA folded into the weights, the time embedding folded into conv1 biases, TwinConv blended, and
+// NHWC activations so that [B,H,W,C] == [B, HW, C] tokens (no permutes around the transformer blocks).
+#include "engine.cuh"
+
+namespace i2it {
+
+static inline int ceil_div_i(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+#define DISPATCH_T(dt, ...)                                   \
+  do {                                                        \
+    if ((dt) == DT_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else { using T = __half; __VA_ARGS__; }                   \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ VAE
+Act Engine::vae_resnet(Plan& P, const std::string& p, const Act& x) {
+  Act h = group_norm(P, x, norm(p + ".norm1"), 1e-6f, true);
+  h = conv(P, h, prep(p + ".conv1", {p + ".conv1"}), ConvOpts());
+  h = group_norm(P, h, norm(p + ".norm2"), 1e-6f, true);
+  Act sc = x;
+  if (has(p + ".conv_shortcut.weight")) {
+    ConvOpts o1; o1.ksize = 1;
+    sc = conv(P, x, prep(p + ".conv_shortcut", {p + ".conv_shortcut"}), o1);
+  }
+  ConvOpts o; o.res = &sc;
+  return conv(P, h, prep(p + ".conv2", {p + ".conv2"}), o);
+}
+
+Act Engine::vae_attn(Plan& P, const std::string& p, const Act& x) {
+  // diffusers Attention (1 head, d = C) with residual; tokens are the NHWC pixels
+  const int C = x.C, B = x.N, N = x.H * x.W;
+  Act t = group_norm(P, x, norm(p + ".group_norm"), 1e-6f, false);
+  Act qk = linear(P, t, prep(p + ".qk", {p + ".to_q", p + ".to_k"}));
+  Act vt = vt_proj(P, t, B, N, prep(p + ".to_v", {p + ".to_v"}));
+  Act a = attention(P, qk.slice(0, C), qk.slice(C, C), vt, B, N, N, 1, C, B);
+  a.N = x.N; a.H = x.H; a.W = x.W;
+  return linear(P, a, prep(p + ".to_out.0", {p + ".to_out.0"}), &x);
+}
+
+Act Engine::build_vae_encoder(Plan& P, const std::string& vp, int B, int H, int W, std::vector<Act>& skips) {
+  const std::string e = vp + "encoder";
+  Act x8 = alloc_act(P, B, H, W, 8, 8, true);
+  {
+    const long long HW = static_cast<long long>(H) * W, total = HW * B;
+    uint16_t* yp = x8.p;
+    Plan* plan = &P;
+    const int dt = dtype;
+    add_op(P, [=](cudaStream_t st) {
+      DISPATCH_T(dt, (pack_input_kernel<T><<<ceil_div_i(total, 256), 256, 0, st>>>(
+                         reinterpret_cast<const T*>(plan->io.x), reinterpret_cast<T*>(yp), 3, HW, total)));
+    });
+  }
+  Act s = conv(P, x8, prep(e + ".conv_in", {e + ".conv_in"}), ConvOpts());
+  for (int i = 0; i < 4; ++i) {
+    skips.push_back(s);                                   // model.py:18-20: the INPUT of each down block
+    mark(P, "skip" + std::to_string(i), s);
+    for (int j = 0; j < 2; ++j) s = vae_resnet(P, e + ".down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), s);
+    if (i < 3) {
+      ConvOpts o; o.stride = 2; o.asym = true;
+      const std::string d = e + ".down_blocks." + std::to_string(i) + ".downsamplers.0.conv";
+      s = conv(P, s, prep(d, {d}), o);
+    }
+  }
+  s = vae_resnet(P, e + ".mid_block.resnets.0", s);
+  s = vae_attn(P, e + ".mid_block.attentions.0", s);
+  s = vae_resnet(P, e + ".mid_block.resnets.1", s);
+  mark(P, "enc_mid", s);
+  s = group_norm(P, s, norm(e + ".conv_norm_out"), 1e-6f, true);
+  s = conv(P, s, prep(e + ".conv_out", {e + ".conv_out"}), ConvOpts());
+  ConvOpts o1; o1.ksize = 1;
+  Act mom = conv(P, s, prep(vp + "quant_conv", {vp + "quant_conv"}), o1);
+  mark(P, "moments", mom);
+  Act z = alloc_act(P, B, H / 8, W / 8, 8, 8, true);
+  {
+    const long long HW = static_cast<long long>(H / 8) * (W / 8), total = HW * B;
+    const uint16_t* mp = mom.p;
+    const int ldm = mom.ld, dt = dtype;
+    uint16_t* zp = z.p;
+    Plan* plan = &P;
+    const float sf = cfg.scaling_factor;
+    P.keep.push_back(mom.hold);
+    add_op(P, [=](cudaStream_t st) {
+      DISPATCH_T(dt, (latent_sample_kernel<T><<<ceil_div_i(total, 128), 128, 0, st>>>(
+                         reinterpret_cast<const T*>(mp), ldm, reinterpret_cast<const T*>(plan->io.eps),
+                         reinterpret_cast<const T*>(plan->io.noise), plan->io.r, sf, reinterpret_cast<T*>(zp), HW, total)));
+    });
+  }
+  mark(P, "latent", z);
+  return z;
+}
+
+void Engine::build_vae_decoder(Plan& P, const std::string& vp, const Act& dec_in, std::vector<Act>& skips) {
+  const std::string d = vp + "decoder";
+  ConvOpts o1; o1.ksize = 1;
+  Act s = conv(P, dec_in, prep(vp + "post_quant_conv", {vp + "post_quant_conv"}), o1);
+  s = conv(P, s, prep(d + ".conv_in", {d + ".conv_in"}), ConvOpts());
+  s = vae_resnet(P, d + ".mid_block.resnets.0", s);
+  s = vae_attn(P, d + ".mid_block.attentions.0", s);
+  s = vae_resnet(P, d + ".mid_block.resnets.1", s);
+  mark(P, "dec_mid", s);
+  for (int i = 0; i < 4; ++i) {
+    // sample = sample + skip_conv_i(skip * gamma): gamma folded into the (bias-free) 1x1 weights, add fused as residual
+    const std::string sk = d + ".skip_conv_" + std::to_string(i + 1);
+    ConvOpts os; os.ksize = 1; os.res = &s;
+    Act skip = skips[3 - i];
+    Act s2 = conv(P, skip, prep(sk, {sk}, false, skip_gamma_), os);
+    skips[3 - i] = Act();                                 // last use: let the pool reclaim it
+    s = s2;
+    for (int j = 0; j < 3; ++j) s = vae_resnet(P, d + ".up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), s);
+    if (i < 3) {
+      s = upsample2x(P, s);
+      const std::string u = d + ".up_blocks." + std::to_string(i) + ".upsamplers.0.conv";
+      s = conv(P, s, prep(u, {u}), ConvOpts());
+    }
+    mark(P, "dec_up" + std::to_string(i), s);
+  }
+  s = group_norm(P, s, norm(d + ".conv_norm_out"), 1e-6f, true);
+  ConvOpts oo; oo.act = TG_ACT_CLAMP1; oo.to_io_out_nchw = true;
+  conv(P, s, prep(d + ".conv_out", {d + ".conv_out"}), oo);
+}
+
+// ------------------------------------------------------------------------------------------ UNet
+Act Engine::unet_resnet(Plan& P, const std::string& p, const Act& x) {
+  Act h = group_norm(P, x, norm(p + ".norm1"), 1e-5f, true);
+  // t == 999 always: time_emb_proj(silu(emb)) is a per-channel constant -> part of conv1's bias
+  h = conv(P, h, prep(p + ".conv1", {p + ".conv1"}, false, 1.f, temb_bias(p)), ConvOpts());
+  h = group_norm(P, h, norm(p + ".norm2"), 1e-5f, true);
+  Act sc = x;
+  if (has(p + ".conv_shortcut.weight")) {
+    ConvOpts o1; o1.ksize = 1;
+    sc = conv(P, x, prep(p + ".conv_shortcut", {p + ".conv_shortcut"}), o1);
+  }
+  ConvOpts o; o.res = &sc;
+  return conv(P, h, prep(p + ".conv2", {p + ".conv2"}), o);
+}
+
+Act Engine::unet_xformer(Plan& P, const std::string& p, const Act& x, int heads, int text_batch) {
+  const int C = x.C, B = x.N, N = x.H * x.W, d = C / heads;
+  const std::string b = p + ".transformer_blocks.0";
+  Act t = group_norm(P, x, norm(p + ".norm"), 1e-6f, false);
+  t = linear(P, t, prep(p + ".proj_in", {p + ".proj_in"}));
+  {  // self-attention
+    Act n = layer_norm(P, t, norm(b + ".norm1"));
+    Act qk = linear(P, n, prep(b + ".attn1.qk", {b + ".attn1.to_q", b + ".attn1.to_k"}));
+    Act vt = vt_proj(P, n, B, N, prep(b + ".attn1.to_v", {b + ".attn1.to_v"}));
+    Act a = attention(P, qk.slice(0, C), qk.slice(C, C), vt, B, N, N, heads, d, B);
+    a.N = x.N; a.H = x.H; a.W = x.W;
+    t = linear(P, a, prep(b + ".attn1.to_out.0", {b + ".attn1.to_out.0"}), &t);
+  }
+  {  // cross-attention over the 77 text tokens
+    Act n = layer_norm(P, t, norm(b + ".norm2"));
+    Act q = linear(P, n, prep(b + ".attn2.to_q", {b + ".attn2.to_q"}));
+    Act k2 = linear(P, text_, prep(b + ".attn2.to_k", {b + ".attn2.to_k"}));
+    Act v2t = vt_proj(P, text_, text_batch, 77, prep(b + ".attn2.to_v", {b + ".attn2.to_v"}));
+    Act a = attention(P, q, k2, v2t, B, N, 77, heads, d, text_batch);
+    a.N = x.N; a.H = x.H; a.W = x.W;
+    t = linear(P, a, prep(b + ".attn2.to_out.0", {b + ".attn2.to_out.0"}), &t);
+  }
+  {  // GEGLU feed-forward: h * gelu(g) fused into the first projection's epilogue (weight rows interleaved)
+    Act n = layer_norm(P, t, norm(b + ".norm3"));
+    Act g = linear(P, n, prep(b + ".ff.net.0.proj", {b + ".ff.net.0.proj"}, true), nullptr, TG_ACT_GEGLU);
+    t = linear(P, g, prep(b + ".ff.net.2", {b + ".ff.net.2"}), &t);
+  }
+  return linear(P, t, prep(p + ".proj_out", {p + ".proj_out"}), &x);
+}
+
+Act Engine::build_unet(Plan& P, const Act& z, int text_batch) {
+  const std::string u = "unet";
+  const int* ch = cfg.unet_channels;
+  const int* heads = cfg.unet_heads;
+  // stage the text embedding: its projections are TMA operands, whose maps need a fixed base address
+  text_ = alloc_act(P, text_batch, 1, 77, cfg.cross_dim);
+  P.keep.push_back(text_.hold);
+  {
+    uint16_t* tp = text_.p;
+    const size_t bytes = static_cast<size_t>(text_batch) * 77 * cfg.cross_dim * 2;
+    Plan* plan = &P;
+    add_op(P, [=](cudaStream_t st) { cudaMemcpyAsync(tp, plan->io.text, bytes, cudaMemcpyDeviceToDevice, st); });
+  }
+  Act s;
+  if (has(u + ".conv_in.conv_in_pretrained.weight")) {
+    s = conv(P, z, prep_twin(u + ".conv_in.conv_in_pretrained", u + ".conv_in.conv_in_curr", twin_r_), ConvOpts());
+  } else {
+    s = conv(P, z, prep(u + ".conv_in", {u + ".conv_in"}), ConvOpts());
+  }
+  std::vector<Act> res{s};
+  for (int i = 0; i < 4; ++i) {
+    const std::string blk = u + ".down_blocks." + std::to_string(i);
+    for (int j = 0; j < 2; ++j) {
+      s = unet_resnet(P, blk + ".resnets." + std::to_string(j), s);
+      if (i < 3) s = unet_xformer(P, blk + ".attentions." + std::to_string(j), s, heads[i], text_batch);
+      res.push_back(s);
+    }
+    if (i < 3) {
+      ConvOpts o; o.stride = 2;
+      s = conv(P, s, prep(blk + ".downsamplers.0.conv", {blk + ".downsamplers.0.conv"}), o);
+      res.push_back(s);
+    }
+  }
+  s = unet_resnet(P, u + ".mid_block.resnets.0", s);
+  s = unet_xformer(P, u + ".mid_block.attentions.0", s, heads[3], text_batch);
+  s = unet_resnet(P, u + ".mid_block.resnets.1", s);
+  mark(P, "unet_mid", s);
+  for (int i = 0; i < 4; ++i) {
+    const std::string blk = u + ".up_blocks." + std::to_string(i);
+    const int hcount = heads[3 - i];
+    for (int j = 0; j < 3; ++j) {
+      Act skip = res.back();
+      res.pop_back();
+      Act cat = alloc_act(P, s.N, s.H, s.W, s.C + skip.C);       // torch.cat([h, skip], dim=1)
+      copy_channels(P, s, cat.slice(0, s.C));
+      copy_channels(P, skip, cat.slice(s.C, skip.C));
+      skip = Act();
+      s = unet_resnet(P, blk + ".resnets." + std::to_string(j), cat);
+      if (i > 0) s = unet_xformer(P, blk + ".attentions." + std::to_string(j), s, hcount, text_batch);
+    }
+    if (i < 3) {
+      s = upsample2x(P, s);
+      s = conv(P, s, prep(blk + ".upsamplers.0.conv", {blk + ".upsamplers.0.conv"}), ConvOpts());
+    }
+  }
+  I2IT_CHECK(res.empty(), "unet: residual stack not consumed");
+  (void)ch;
+  s = group_norm(P, s, norm(u + ".conv_norm_out"), 1e-5f, true);
+  s = conv(P, s, prep(u + ".conv_out", {u + ".conv_out"}), ConvOpts());
+  text_ = Act();
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------ whole path
+Plan* Engine::plan_for(int B, int H, int W, int direction, int text_batch) {
+  const std::vector<int> key{B, H, W, direction, text_batch};
+  auto it = plans_.find(key);
+  if (it != plans_.end()) return it->second.get();
+  I2IT_CHECK(finalized_, "i2it_finalize_weights must be called before a forward");
+  std::string vp = "vae.";
+  if (cfg.model_kind == I2IT_CYCLEGAN && direction == I2IT_B2A) vp = "vae_b2a.";
+  std::unique_ptr<Plan> up(new Plan());
+  Plan& P = *up;
+  std::vector<Act> skips;
+  Act z = build_vae_encoder(P, vp, B, H, W, skips);
+  Act pred = build_unet(P, z, text_batch);
+  mark(P, "model_pred", pred);
+  Act dec_in = alloc_act(P, B, H / 8, W / 8, 8, 8, true);
+  {
+    // alpha_bar_999 of the scaled-linear schedule (fp32 cumprod, as diffusers computes it): 0.0046600951
+    const float sa = 0.06826488673686981f, s1 = 0.9976672530174255f, inv_sf = 1.0f / cfg.scaling_factor;
+    const long long HW = static_cast<long long>(H / 8) * (W / 8), total = HW * B;
+    const uint16_t* zp = z.p;
+    const uint16_t* pp = pred.p;
+    uint16_t* dp = dec_in.p;
+    const int ldp = pred.ld, dt = dtype;
+    Plan* plan = &P;
+    P.keep.push_back(z.hold);
+    P.keep.push_back(pred.hold);
+    add_op(P, [=](cudaStream_t st) {
+      DISPATCH_T(dt, (ddpm_step_kernel<T><<<ceil_div_i(total, 128), 128, 0, st>>>(
+                         reinterpret_cast<const T*>(zp), reinterpret_cast<const T*>(pp), ldp, s1, sa, inv_sf,
+                         reinterpret_cast<T*>(dp), reinterpret_cast<T*>(plan->io.out_latent), HW, total)));
+    });
+  }
+  mark(P, "dec_in", dec_in);
+  build_vae_decoder(P, vp, dec_in, skips);
+  I2IT_CUDA(cudaDeviceSynchronize());       // weight preparation ran on the default stream
+  I2IT_CUDA(cudaGetLastError());
+  Plan* raw_plan = up.get();
+  plans_[key] = std::move(up);
+  return raw_plan;
+}
+
+}  // namespace i2it

@@ -1,0 +1,373 @@
+// tapgemm: the one tensor-core kernel of the path.
+//
+//   D[m, n] = act( alpha * sum_{tap t} sum_k A_t[m, k] * B_t[n, k]  + bias ) + residual
+//
+// A_t is a TMA *box* of the activation tensor shifted by the tap's spatial offset, so a 3x3 /
+// stride-2 / 1x1 convolution, a linear layer and the attention GEMMs (Q K^T, P V, V^T = W X^T)
+// are all the same implicit GEMM.  Zero padding, ragged edges and channel padding come from TMA
+// out-of-bounds zero fill, never from materialised copies.
+//
+// sm_100a structure (one persistent CTA per SM, 192 threads):
+//   warp 4 lane 0 : TMA producer   cp.async.bulk.tensor.5d -> 128B-swizzled smem ring (4 stages)
+//   warp 5 lane 0 : MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN<=256, K=16
+//                                  accumulators in TMEM (2 stages x 256 fp32 columns)
+//   warps 0..3    : epilogue       tcgen05.ld 32x32b -> bias/residual/GEGLU/clamp -> global
+//   mbarriers     : full/empty per smem stage, tmem_full/tmem_empty per accumulator stage
+//
+// Replaces (reference call sites): every nn.Conv2d / nn.Linear / SDPA matmul under
+// vae.encode / unet(...) / vae.decode at /root/reference/src/pix2pix_turbo.py:198-203, which
+// dispatch to cuDNN implicit GEMM, cuBLAS and flash/mem-efficient SDPA in the reference stack.
+#pragma once
+#include "common.cuh"
+
+namespace i2it {
+
+constexpr int TG_BM = 128;             // rows per tile (= TMEM lanes)
+constexpr int TG_BK = 64;              // K elements per stage (= 128 B = one swizzle atom)
+constexpr int TG_STAGES = 4;
+constexpr int TG_MAX_TAPS = 16;
+constexpr int TG_A_STAGE = TG_BM * TG_BK * 2;    // 16 KiB
+constexpr int TG_B_STAGE = 256 * TG_BK * 2;      // 32 KiB (BN <= 256)
+constexpr int TG_BAR_BYTES = 256;
+constexpr int TG_SMEM = TG_STAGES * (TG_A_STAGE + TG_B_STAGE) + TG_BAR_BYTES + 1024;  // +1024: manual alignment
+constexpr int TG_THREADS = 192;
+constexpr int TG_ACC_COLS = 256;       // TMEM columns per accumulator stage
+
+enum TgAct : int { TG_ACT_NONE = 0, TG_ACT_CLAMP1 = 1, TG_ACT_GEGLU = 2 };
+enum TgBias : int { TG_BIAS_NONE = 0, TG_BIAS_COL = 1, TG_BIAS_ROW = 2 };
+
+struct TapGemmParams {
+  // ---- tile space: 4 "row" dims d1..d4 of the A tensor map (d0 is K) ----
+  int tdim[4];     // tiles per dim
+  int box[4];      // A box extent per dim, prod == 128; row r of a tile = j1 + box0*(j2 + box1*(j3 + box2*j4))
+  int ext[4];      // logical extent per dim: row valid iff t*box + j < ext
+  int a_mul[4];    // A coordinate(d) = t_d * a_mul[d] + tap_a[tap][d+1]
+  int b_mul[3];    // B coordinate(2..4) = t_{2..4} * b_mul + tap_b[tap][1..3]
+  int n_tiles, BN, N;
+  int num_taps, kchunks;
+  int tap_a[TG_MAX_TAPS][5];
+  int tap_b[TG_MAX_TAPS][4];
+  uint32_t idesc;
+  // ---- epilogue ----
+  void* out;
+  long long ostride[4];   // elements
+  long long ocol;         // element stride between consecutive output columns (1 = contiguous)
+  int out_fp32;
+  const void* res;        // optional residual, element type == activation type
+  long long rstride[4];
+  long long rcol;
+  const float* bias;
+  int bias_mode;
+  float alpha;
+  int act;
+  int* err;               // device error word (watchdog)
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug must surface as a trapped launch with an error word, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
+      if (err) atomicExch(err, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), start address
+// advanced by 32 B per UMMA_K=16 step inside the swizzle atom.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;   // stride byte offset between 8-row core-matrix groups
+  d |= static_cast<uint64_t>(1) << 46;           // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;           // SWIZZLE_128B
+  return d;
+}
+
+// host: instruction descriptor for kind::f16 (A,B fp16 or bf16 K-major, D fp32), M=128, N=bn
+inline uint32_t make_idesc(int dtype, int bn) {
+  uint32_t fmt = (dtype == DT_BF16) ? 1u : 0u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(bn >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+struct TileCoord {
+  int nt, t[4];
+};
+__device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int tile) {
+  TileCoord c;
+  c.nt = tile % p.n_tiles;
+  int r = tile / p.n_tiles;
+  c.t[0] = r % p.tdim[0]; r /= p.tdim[0];
+  c.t[1] = r % p.tdim[1]; r /= p.tdim[1];
+  c.t[2] = r % p.tdim[2]; r /= p.tdim[2];
+  c.t[3] = r;
+  return c;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TG_THREADS, 1)
+tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ TapGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = base + TG_STAGES * TG_A_STAGE;
+  const uint32_t bars = sB + TG_STAGES * TG_B_STAGE;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (TG_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * TG_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * TG_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * TG_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.n_tiles * p.tdim[0] * p.tdim[1] * p.tdim[2] * p.tdim[3];
+  const int steps = p.num_taps * p.kchunks;
+
+  if (warp == 4 && lane == 0) {
+    for (int s = 0; s < TG_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 4) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      const uint32_t tx_bytes = TG_A_STAGE + static_cast<uint32_t>(p.BN) * (TG_BK * 2);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord c = decode_tile(p, tile);
+        const int a1 = c.t[0] * p.a_mul[0], a2 = c.t[1] * p.a_mul[1], a3 = c.t[2] * p.a_mul[2],
+                  a4 = c.t[3] * p.a_mul[3];
+        const int b2 = c.t[1] * p.b_mul[0], b3 = c.t[2] * p.b_mul[1], b4 = c.t[3] * p.b_mul[2];
+        const int n0 = c.nt * p.BN;
+        for (int t = 0; t < p.num_taps; ++t) {
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(empty_bar(stage), phase ^ 1, p.err, 1);
+            mbar_expect_tx(full_bar(stage), tx_bytes);
+            tma_load_5d(sA + stage * TG_A_STAGE, &tmA, full_bar(stage), kc * TG_BK + p.tap_a[t][0],
+                        a1 + p.tap_a[t][1], a2 + p.tap_a[t][2], a3 + p.tap_a[t][3], a4 + p.tap_a[t][4]);
+            tma_load_5d(sB + stage * TG_B_STAGE, &tmB, full_bar(stage), kc * TG_BK + p.tap_b[t][0], n0,
+                        b2 + p.tap_b[t][1], b3 + p.tap_b[t][2], b4 + p.tap_b[t][3]);
+            if (++stage == TG_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      int stage = 0, phase = 0, iter = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        const int acc = iter & 1, aphase = (iter >> 1) & 1;
+        mbar_wait(tempty_bar(acc), aphase ^ 1, p.err, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TG_ACC_COLS;
+        for (int s = 0; s < steps; ++s) {
+          mbar_wait(full_bar(stage), phase, p.err, 3);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(sA + stage * TG_A_STAGE);
+          const uint64_t bdesc = umma_desc_sw128(sB + stage * TG_B_STAGE);
+#pragma unroll
+          for (int k = 0; k < TG_BK / 16; ++k)
+            tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (s > 0 || k > 0) ? 1u : 0u);
+          tc_commit(empty_bar(stage));               // frees the smem slot when these MMAs retire
+          if (++stage == TG_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar(acc));                   // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ================================ epilogue (warps 0..3) ================================
+    const int row = warp * 32 + lane;
+    int rr = row;
+    const int j1 = rr % p.box[0]; rr /= p.box[0];
+    const int j2 = rr % p.box[1]; rr /= p.box[1];
+    const int j3 = rr % p.box[2];
+    const int j4 = rr / p.box[2];
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      const int acc = iter & 1, aphase = (iter >> 1) & 1;
+      const TileCoord c = decode_tile(p, tile);
+      const int g1 = c.t[0] * p.box[0] + j1, g2 = c.t[1] * p.box[1] + j2, g3 = c.t[2] * p.box[2] + j3,
+                g4 = c.t[3] * p.box[3] + j4;
+      const bool row_ok = (g1 < p.ext[0]) && (g2 < p.ext[1]) && (g3 < p.ext[2]) && (g4 < p.ext[3]);
+      const long long obase = g1 * p.ostride[0] + g2 * p.ostride[1] + g3 * p.ostride[2] + g4 * p.ostride[3];
+      const long long rbase = g1 * p.rstride[0] + g2 * p.rstride[1] + g3 * p.rstride[2] + g4 * p.rstride[3];
+      const float rbias = (p.bias_mode == TG_BIAS_ROW && row_ok) ? p.bias[g1] : 0.0f;
+      const int n0 = c.nt * p.BN;
+
+      mbar_wait(tfull_bar(acc), aphase, p.err, 4);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * TG_ACC_COLS;
+
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t raw[16];
+        __syncwarp();                                // tcgen05.ld is .sync.aligned: reconverge after the guarded stores
+        tc_ld16(taddr + c0, raw);
+        tc_wait_ld();
+        const int col0 = n0 + c0;
+        if (!row_ok || col0 >= p.N) continue;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
+        if (p.bias_mode == TG_BIAS_COL) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) if (col0 + i < p.N) v[i] += p.bias[col0 + i];
+        } else if (p.bias_mode == TG_BIAS_ROW) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += rbias;
+        }
+        const bool full = (col0 + 16 <= p.N);
+        if (p.act == TG_ACT_GEGLU) {
+          // interleaved columns (2j, 2j+1) = (h_j, gate_j) -> out column j = h * gelu(gate)
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = v[2 * i] * gelu_erf_f(v[2 * i + 1]);
+          T* optr = reinterpret_cast<T*>(p.out) + obase + (col0 >> 1);
+          if (p.res) {
+            const T* rptr = reinterpret_cast<const T*>(p.res) + rbase + (col0 >> 1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] += Elem<T>::to_f(rptr[i]);
+          }
+          if (full && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0)) {
+            uint4 u;
+            u.x = Elem<T>::pack(o[0], o[1]); u.y = Elem<T>::pack(o[2], o[3]);
+            u.z = Elem<T>::pack(o[4], o[5]); u.w = Elem<T>::pack(o[6], o[7]);
+            st16(optr, u);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (col0 + 2 * i + 1 < p.N) optr[i] = Elem<T>::from_f(o[i]);
+          }
+          continue;
+        }
+        if (p.res) {
+          const T* rptr = reinterpret_cast<const T*>(p.res) + rbase + col0 * p.rcol;
+          if (full && p.rcol == 1 && ((reinterpret_cast<uintptr_t>(rptr) & 15) == 0)) {
+            const uint4 r0 = ld_nc16(rptr), r1 = ld_nc16(rptr + 8);
+            const uint32_t ru[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 f = Elem<T>::unpack(ru[i]);
+              v[2 * i] += f.x; v[2 * i + 1] += f.y;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (col0 + i < p.N) v[i] += Elem<T>::to_f(rptr[i * p.rcol]);
+          }
+        }
+        if (p.act == TG_ACT_CLAMP1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fminf(fmaxf(v[i], -1.0f), 1.0f);
+        }
+        if (p.out_fp32) {
+          float* optr = reinterpret_cast<float*>(p.out) + obase + col0 * p.ocol;
+          if (full && p.ocol == 1 && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<float4*>(optr + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (col0 + i < p.N) optr[i * p.ocol] = v[i];
+          }
+        } else {
+          T* optr = reinterpret_cast<T*>(p.out) + obase + col0 * p.ocol;
+          if (full && p.ocol == 1 && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0)) {
+            uint4 u0, u1;
+            u0.x = Elem<T>::pack(v[0], v[1]);   u0.y = Elem<T>::pack(v[2], v[3]);
+            u0.z = Elem<T>::pack(v[4], v[5]);   u0.w = Elem<T>::pack(v[6], v[7]);
+            u1.x = Elem<T>::pack(v[8], v[9]);   u1.y = Elem<T>::pack(v[10], v[11]);
+            u1.z = Elem<T>::pack(v[12], v[13]); u1.w = Elem<T>::pack(v[14], v[15]);
+            st16(optr, u0);
+            st16(optr + 8, u1);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (col0 + i < p.N) optr[i * p.ocol] = Elem<T>::from_f(v[i]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+}  // namespace i2it
