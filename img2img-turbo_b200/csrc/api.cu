@@ -115,6 +115,15 @@ int i2it_launch_count(i2it_handle* h, int batch, int H, int W, int direction, in
   API_END
 }
 
+int i2it_profile(i2it_handle* h, int reps, char* json, size_t cap, void* stream) {
+  API_BEGIN(h)
+  I2IT_CHECK(json != nullptr && cap > 2 && reps > 0, "i2it_profile: bad arguments");
+  const std::string js = E.profile_json(reps, static_cast<cudaStream_t>(stream));
+  I2IT_CHECK(js.size() + 1 <= cap, "i2it_profile: buffer too small (" + std::to_string(js.size() + 1) + " bytes needed)");
+  std::memcpy(json, js.c_str(), js.size() + 1);
+  API_END
+}
+
 int i2it_read_stage(i2it_handle* h, const char* name, float* dst, size_t dst_elems, int dims[4]) {
   API_BEGIN(h)
   E.read_stage(name, dst, dst_elems, dims);

@@ -80,6 +80,15 @@ void* Pool::get(size_t bytes, size_t* actual) {
   return p;
 }
 
+void* Pool::get_fresh(size_t bytes) {
+  bytes = (bytes + 511) / 512 * 512;
+  void* p = nullptr;
+  I2IT_CUDA(cudaMalloc(&p, bytes));
+  blocks.emplace_back(p, bytes);
+  total += bytes;
+  return p;
+}
+
 // ---------------------------------------------------------------------------------------------
 // engine basics
 // ---------------------------------------------------------------------------------------------
@@ -105,6 +114,9 @@ Engine::Engine(const i2it_config& c) : cfg(c), dtype(c.dtype) {
   *h = 0;
   I2IT_CUDA(cudaHostGetDevicePointer(&d_err, h, 0));
   err_host_ = h;
+  I2IT_CUDA(cudaStreamCreateWithFlags(&gstream_, cudaStreamNonBlocking));
+  I2IT_CUDA(cudaEventCreateWithFlags(&ev_in_, cudaEventDisableTiming));
+  I2IT_CUDA(cudaEventCreateWithFlags(&ev_out_, cudaEventDisableTiming));
   encode_fn();
 }
 
@@ -114,6 +126,9 @@ Engine::~Engine() {
   for (auto& kv : w_) cudaFree(kv.second.d);
   if (scratch_) cudaFree(scratch_);
   if (err_host_) cudaFreeHost(err_host_);
+  if (gstream_) cudaStreamDestroy(gstream_);
+  if (ev_in_) cudaEventDestroy(ev_in_);
+  if (ev_out_) cudaEventDestroy(ev_out_);
 }
 
 void Engine::check_device_error() {
@@ -356,12 +371,17 @@ Act Engine::alloc_act(Plan& P, int N, int H, int W, int C, int ld, bool zero_per
   Act a;
   a.N = N; a.H = H; a.W = W; a.C = C; a.ld = ld ? ld : C;
   const size_t bytes = static_cast<size_t>(N) * H * W * a.ld * 2;
+  if (zero_persistent) {
+    // A recycled block would be dirtied at RUN time by the earlier ops that used it (the memset below runs once, at
+    // build time), so padded small-channel tensors get their own allocation for the plan's lifetime.
+    void* p = P.pool.get_fresh(bytes);
+    I2IT_CUDA(cudaMemset(p, 0, bytes));
+    a.hold = std::shared_ptr<void>(p, [](void*) {});
+    a.p = static_cast<uint16_t*>(p);
+    return a;
+  }
   a.hold = alloc_raw(P, bytes);
   a.p = static_cast<uint16_t*>(a.hold.get());
-  if (zero_persistent) {
-    I2IT_CUDA(cudaMemset(a.p, 0, bytes));
-    P.keep.push_back(a.hold);      // never returns to the pool: the zero padding must survive
-  }
   return a;
 }
 
@@ -381,14 +401,18 @@ int Engine::pick_bn(long long m_tiles, int N, bool) const {
 }
 
 void Engine::launch_gemm(Plan& P, const CUtensorMap& ta, const CUtensorMap& tb, const TapGemmParams& p, int grid,
-                         bool out_from_io) {
+                         bool out_from_io, const char* kind, double k_valid, double bytes) {
   const int dt = dtype;
   Plan* plan = &P;
+  const double m_valid = 1.0 * p.ext[0] * p.ext[1] * p.ext[2] * p.ext[3];
+  char shp[160];
+  snprintf(shp, sizeof shp, "M=%.0f N=%d K=%.0f taps=%d BN=%d tiles=%d grid=%d", m_valid, p.N, k_valid, p.num_taps, p.BN,
+           p.n_tiles * p.tdim[0] * p.tdim[1] * p.tdim[2] * p.tdim[3], grid);
   add_op(P, [ta, tb, p, grid, dt, out_from_io, plan](cudaStream_t st) {
     TapGemmParams q = p;
     if (out_from_io) q.out = plan->io.out;
     DISPATCH_T(dt, (tapgemm_kernel<T><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, q)));
-  });
+  }, kind, 2.0 * m_valid * p.N * k_valid, bytes, shp);
 }
 
 static void fill_strides(TmapSpec& s) {
@@ -516,7 +540,13 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o) {
 
   const CUtensorMap ta = encode_tmap(sa, dtype), tb = encode_tmap(sb, dtype);
   const int grid = static_cast<int>(std::min<long long>(m_tiles * p.n_tiles, num_sms));
-  launch_gemm(P, ta, tb, p, grid, o.to_io_out_nchw);
+  {
+    const double m_valid = 1.0 * x.N * Ho * Wo, k_valid = 1.0 * taps * w.cin;
+    const double bytes = 2.0 * (1.0 * x.N * x.H * x.W * w.cin + m_valid * outc * (o.out_fp32 ? 2 : 1) + 1.0 * gemm_n * k_valid +
+                                (o.res ? m_valid * outc : 0));
+    const char* kind = (k == 3) ? (o.stride == 2 ? "tapgemm:conv3x3s2" : "tapgemm:conv3x3") : "tapgemm:linear";
+    launch_gemm(P, ta, tb, p, grid, o.to_io_out_nchw, kind, k_valid, bytes);
+  }
   return out;
 }
 
@@ -550,16 +580,16 @@ Act Engine::group_norm(Plan& P, const Act& x, const NormW& nw, float eps, bool s
   const float* g = nw.g;
   const float* b = nw.b;
   add_op(P, [=](cudaStream_t st) {
-    DISPATCH_T(dt, (gn_stats_kernel<T><<<dim3(chunks, N), threads, 2 * C * sizeof(float), st>>>(
+    DISPATCH_T(dt, (gn_stats_kernel<T><<<dim3(chunks, N), threads, static_cast<size_t>(rows) * 2 * C * sizeof(float), st>>>(
                        reinterpret_cast<const T*>(xp), ximg, ldx, C, HW, cg, pix, d_part)));
-  });
+  }, "gn_stats", 0, 2.0 * N * HW * C);
   const double inv_count = 1.0 / (static_cast<double>(HW) * cg);
-  add_op(P, [=](cudaStream_t st) { gn_finalize_kernel<<<N, 32, 0, st>>>(d_part, chunks, inv_count, eps, d_stats); });
+  add_op(P, [=](cudaStream_t st) { gn_finalize_kernel<<<N, 32, 0, st>>>(d_part, chunks, inv_count, eps, d_stats); }, "gn_final");
   add_op(P, [=](cudaStream_t st) {
     DISPATCH_T(dt, (gn_apply_kernel<T><<<dim3(chunks, N), threads, 0, st>>>(
                        reinterpret_cast<const T*>(xp), ximg, ldx, reinterpret_cast<T*>(yp), yimg, ldy, C, HW, cg, pix,
                        d_stats, g, b, isilu)));
-  });
+  }, "gn_apply", 0, 4.0 * N * HW * C);
   return y;
 }
 
@@ -576,7 +606,7 @@ Act Engine::layer_norm(Plan& P, const Act& x, const NormW& nw) {
     DISPATCH_T(dt, (layernorm_kernel<T><<<ceil_div(rows * 32, 256), 256, 0, st>>>(
                        reinterpret_cast<const T*>(xp), ldx, reinterpret_cast<T*>(yp), ldy, static_cast<int>(rows), C, g, b,
                        1e-5f)));
-  });
+  }, "layernorm", 0, 4.0 * rows * C);
   return y;
 }
 
@@ -586,10 +616,11 @@ Act Engine::upsample2x(Plan& P, const Act& x) {
   const uint16_t* xp = x.p;
   uint16_t* yp = y.p;
   const int ldx = x.ld, ldy = y.ld, H = x.H, W = x.W, C = x.C, dt = dtype;
+  const double N_ = x.N;
   add_op(P, [=](cudaStream_t st) {
     DISPATCH_T(dt, (upsample2x_kernel<T><<<ceil_div(total, 256), 256, 0, st>>>(reinterpret_cast<const T*>(xp), ldx,
                                                                              reinterpret_cast<T*>(yp), ldy, H, W, C, total)));
-  });
+  }, "upsample2x", 0, 2.0 * 5.0 * N_ * H * W * C);
   return y;
 }
 
@@ -602,7 +633,7 @@ void Engine::copy_channels(Plan& P, const Act& src, const Act& dst) {
   add_op(P, [=](cudaStream_t st) {
     DISPATCH_T(dt, (copy2d_kernel<T><<<ceil_div(total, 256), 256, 0, st>>>(reinterpret_cast<const T*>(xp), ldx,
                                                                          reinterpret_cast<T*>(yp), ldy, C, total)));
-  });
+  }, "concat_copy", 0, 4.0 * total * 8);
 }
 
 Act Engine::vt_proj(Plan& P, const Act& x, int B, int ntok, const PW& wv) {
@@ -643,7 +674,8 @@ Act Engine::vt_proj(Plan& P, const Act& x, int B, int ntok, const PW& wv) {
   p.alpha = 1.f;
   p.err = d_err;
   const CUtensorMap ta = encode_tmap(sa, dtype), tb = encode_tmap(sb, dtype);
-  launch_gemm(P, ta, tb, p, static_cast<int>(std::min<long long>(m_tiles * p.n_tiles, num_sms)), false);
+  launch_gemm(P, ta, tb, p, static_cast<int>(std::min<long long>(m_tiles * p.n_tiles, num_sms)), false, "tapgemm:vt",
+              wv.cin, 2.0 * (1.0 * C * wv.cin + 1.0 * B * ntok * wv.cin + 1.0 * B * C * ntok));
   return vt;
 }
 
@@ -694,7 +726,8 @@ Act Engine::attention(Plan& P, const Act& q, const Act& k, const Act& vt, int B,
     p.alpha = 1.0f / sqrtf(static_cast<float>(d));
     p.err = d_err;
     const CUtensorMap ta = encode_tmap(sa, dtype), tb = encode_tmap(sb, dtype);
-    launch_gemm(P, ta, tb, p, static_cast<int>(std::min<long long>(m_tiles * p.n_tiles, num_sms)), false);
+    launch_gemm(P, ta, tb, p, static_cast<int>(std::min<long long>(m_tiles * p.n_tiles, num_sms)), false, "tapgemm:attn_qk", d,
+                2.0 * B * heads * (1.0 * Nq * d + 1.0 * Nk * d) + 4.0 * rows * Nk);
   }
   {  // P = softmax(S)
     const int dt = dtype;
@@ -702,12 +735,12 @@ Act Engine::attention(Plan& P, const Act& q, const Act& k, const Act& vt, int B,
       add_op(P, [=](cudaStream_t st) {
         DISPATCH_T(dt, (softmax_kernel<T, 128><<<static_cast<unsigned>(rows), 128, 0, st>>>(S, lds, reinterpret_cast<T*>(Pm), lds,
                                                                                           rows, Nk, lds)));
-      });
+      }, "softmax", 0, 6.0 * rows * Nk);
     } else {
       add_op(P, [=](cudaStream_t st) {
         DISPATCH_T(dt, (softmax_kernel<T, 32><<<static_cast<unsigned>((rows + 3) / 4), 128, 0, st>>>(
                            S, lds, reinterpret_cast<T*>(Pm), lds, rows, Nk, lds)));
-      });
+      }, "softmax", 0, 6.0 * rows * Nk);
     }
   }
   {  // O = P V   (V given transposed: [kvB][C][ldv])
@@ -743,7 +776,8 @@ Act Engine::attention(Plan& P, const Act& q, const Act& k, const Act& vt, int B,
     p.alpha = 1.f;
     p.err = d_err;
     const CUtensorMap ta = encode_tmap(sa, dtype), tb = encode_tmap(sb, dtype);
-    launch_gemm(P, ta, tb, p, static_cast<int>(std::min<long long>(m_tiles * p.n_tiles, num_sms)), false);
+    launch_gemm(P, ta, tb, p, static_cast<int>(std::min<long long>(m_tiles * p.n_tiles, num_sms)), false, "tapgemm:attn_pv", Nk,
+                2.0 * (1.0 * rows * Nk + 1.0 * B * heads * Nk * d + 1.0 * rows * d));
   }
   return out;
 }
@@ -759,21 +793,56 @@ void Engine::forward(const IO& io, int B, int H, int W, int direction, int text_
   P->io = io;
   last_plan_ = P;
   if (cfg.use_cuda_graph) {
-    if (!(P->gexec && P->gio == io)) {
-      if (P->gexec) { cudaGraphExecDestroy(P->gexec); P->gexec = nullptr; }
+    // replay on the engine's own stream, ordered after/before the caller's stream with events
+    I2IT_CUDA(cudaEventRecord(ev_in_, st));
+    I2IT_CUDA(cudaStreamWaitEvent(gstream_, ev_in_, 0));
+    cudaGraphExec_t ge = nullptr;
+    for (auto& g : P->graphs) if (g.first == io) ge = g.second;
+    if (!ge) {
+      // pointers are baked into the captured launches: one graph per distinct IO set (the torch allocator recycles blocks,
+      // so a steady-state loop hits this cache)
+      if (P->graphs.size() >= 8) { cudaGraphExecDestroy(P->graphs.front().second); P->graphs.erase(P->graphs.begin()); }
       cudaGraph_t g = nullptr;
-      I2IT_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      for (auto& op : P->ops) op(st);
-      I2IT_CUDA(cudaStreamEndCapture(st, &g));
-      I2IT_CUDA(cudaGraphInstantiate(&P->gexec, g, 0));
+      I2IT_CUDA(cudaStreamBeginCapture(gstream_, cudaStreamCaptureModeThreadLocal));
+      for (auto& op : P->ops) op(gstream_);
+      I2IT_CUDA(cudaStreamEndCapture(gstream_, &g));
+      I2IT_CUDA(cudaGraphInstantiate(&ge, g, 0));
       cudaGraphDestroy(g);
-      P->gio = io;
+      P->graphs.emplace_back(io, ge);
     }
-    I2IT_CUDA(cudaGraphLaunch(P->gexec, st));
+    I2IT_CUDA(cudaGraphLaunch(ge, gstream_));
+    I2IT_CUDA(cudaEventRecord(ev_out_, gstream_));
+    I2IT_CUDA(cudaStreamWaitEvent(st, ev_out_, 0));
   } else {
     for (auto& op : P->ops) op(st);
     I2IT_CUDA(cudaGetLastError());
   }
+}
+
+// Per-launch device timing of the last forward's plan (CUDA events around every op, `reps` passes, averaged).
+std::string Engine::profile_json(int reps, cudaStream_t st) {
+  I2IT_CHECK(last_plan_ != nullptr, "profile: run a forward first");
+  Plan& P = *last_plan_;
+  const size_t n = P.ops.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) I2IT_CUDA(cudaEventCreate(&e));
+  std::vector<double> ms(n, 0.0);
+  for (int r = 0; r < reps; ++r) {
+    I2IT_CUDA(cudaEventRecord(ev[0], st));
+    for (size_t i = 0; i < n; ++i) { P.ops[i](st); I2IT_CUDA(cudaEventRecord(ev[i + 1], st)); }
+    I2IT_CUDA(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < n; ++i) { float t = 0; I2IT_CUDA(cudaEventElapsedTime(&t, ev[i], ev[i + 1])); ms[i] += t / reps; }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  std::string js = "[";
+  char buf[512];
+  for (size_t i = 0; i < n; ++i) {
+    const OpMeta& m = P.meta[i];
+    snprintf(buf, sizeof buf, "%s{\"i\":%zu,\"kind\":\"%s\",\"ms\":%.6f,\"flops\":%.6g,\"bytes\":%.6g,\"shape\":\"%s\"}", i ? "," : "", i,
+             m.kind.c_str(), ms[i], m.flops, m.bytes, m.shape.c_str());
+    js += buf;
+  }
+  return js + "]";
 }
 
 __global__ void stage_to_nchw_f32_kernel(const uint16_t* x, int ld, int C, long long HW, long long total, float* out,

@@ -35,6 +35,7 @@ struct Pool {
   size_t total = 0;
   ~Pool();
   void* get(size_t bytes, size_t* actual);
+  void* get_fresh(size_t bytes);   // never recycled (zero-padded small-channel tensors must stay clean at run time)
   void put(void* p, size_t bytes) { free_.emplace(bytes, p); }
 };
 
@@ -61,15 +62,21 @@ struct IO {
   bool operator==(const IO& o) const { return std::memcmp(this, &o, sizeof(IO)) == 0; }
 };
 
+struct OpMeta {                  // bookkeeping for i2it_profile / bench roofline accounting
+  std::string kind;              // "tapgemm:conv3x3", "gn_apply", ...
+  double flops = 0, bytes = 0;   // ALGORITHMIC work of the launch (2*M*N*K; unique bytes in + out + weights)
+  std::string shape;
+};
+
 struct Plan {
   Pool pool;                                           // declared first: destroyed last
   std::vector<std::function<void(cudaStream_t)>> ops;  // one kernel launch each
+  std::vector<OpMeta> meta;                            // parallel to ops
   std::map<std::string, Act> stages;
   std::vector<std::shared_ptr<void>> keep;
   IO io;
-  cudaGraphExec_t gexec = nullptr;
-  IO gio;
-  ~Plan() { if (gexec) cudaGraphExecDestroy(gexec); }
+  std::vector<std::pair<IO, cudaGraphExec_t>> graphs;  // small cache: one instantiated graph per distinct IO pointer set
+  ~Plan() { for (auto& g : graphs) cudaGraphExecDestroy(g.second); }
 };
 
 struct ConvOpts {
@@ -140,13 +147,21 @@ class Engine {
   Act unet_xformer(Plan& P, const std::string& p, const Act& x, int heads, int text_batch);
   void mark(Plan& P, const std::string& name, const Act& a) { if (cfg.keep_stages) P.stages[name] = a; }
 
-  template <typename F> void add_op(Plan& P, F&& f) { P.ops.emplace_back(std::forward<F>(f)); }
+  template <typename F> void add_op(Plan& P, F&& f, const char* kind = "misc", double flops = 0, double bytes = 0,
+                                    const std::string& shape = "") {
+    P.ops.emplace_back(std::forward<F>(f));
+    OpMeta m; m.kind = kind; m.flops = flops; m.bytes = bytes; m.shape = shape;
+    P.meta.push_back(m);
+  }
   void launch_gemm(Plan& P, const CUtensorMap& ta, const CUtensorMap& tb, const TapGemmParams& p, int grid,
-                   bool out_from_io);
+                   bool out_from_io, const char* kind, double k_valid, double bytes);
+  std::string profile_json(int reps, cudaStream_t st);
   int pick_bn(long long m_tiles, int N, bool even32) const;
 
   int* d_err = nullptr;      // device alias of a mapped host word written by the tapgemm watchdog
   int* err_host_ = nullptr;
+  cudaStream_t gstream_ = nullptr;          // graphs are captured/replayed here (capture is illegal on the legacy stream)
+  cudaEvent_t ev_in_ = nullptr, ev_out_ = nullptr;
   void check_device_error();
 
  private:

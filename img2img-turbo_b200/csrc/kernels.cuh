@@ -15,39 +15,36 @@ namespace i2it {
 template <typename T>
 __global__ void gn_stats_kernel(const T* __restrict__ x, long long img_stride, int ld, int C, int HW, int cg,
                                 int pix_per_cta, float* __restrict__ partial /*[N][chunks][32][2]*/) {
-  extern __shared__ float s_acc[];   // [2*C]
+  extern __shared__ float s_acc[];   // [rows][2][C]: per-row partials, reduced in a fixed order (bit-reproducible)
   const int vecs = C >> 3;
   const int vx = threadIdx.x % vecs, vy = threadIdx.x / vecs, rows = blockDim.x / vecs;
   const int n = blockIdx.y, chunk = blockIdx.x;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   const int p0 = chunk * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
   const T* xb = x + n * img_stride + vx * 8;
-  if (vy < rows) {
-    for (int p = p0 + vy; p < p1; p += rows) {
-      const uint4 u = ld_nc16(xb + static_cast<long long>(p) * ld);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  for (int p = p0 + vy; p < p1; p += rows) {
+    const uint4 u = ld_nc16(xb + static_cast<long long>(p) * ld);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = Elem<T>::unpack(w[i]);
-        s[2 * i] += f.x; q[2 * i] += f.x * f.x;
-        s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&s_acc[vx * 8 + i], s[i]);
-      atomicAdd(&s_acc[C + vx * 8 + i], q[i]);
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = Elem<T>::unpack(w[i]);
+      s[2 * i] += f.x; q[2 * i] += f.x * f.x;
+      s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
     }
   }
+  float* mine = s_acc + static_cast<size_t>(vy) * 2 * C;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { mine[vx * 8 + i] = s[i]; mine[C + vx * 8 + i] = q[i]; }
   __syncthreads();
   if (threadIdx.x < 32) {
     const int g = threadIdx.x;
     float a = 0.f, b = 0.f;
-    for (int c = g * cg; c < (g + 1) * cg; ++c) { a += s_acc[c]; b += s_acc[C + c]; }
+    for (int r = 0; r < rows; ++r) {
+      const float* row = s_acc + static_cast<size_t>(r) * 2 * C;
+      for (int c = g * cg; c < (g + 1) * cg; ++c) { a += row[c]; b += row[C + c]; }
+    }
     float* o = partial + ((static_cast<long long>(n) * gridDim.x + chunk) * 32 + g) * 2;
     o[0] = a; o[1] = b;
   }

@@ -27,7 +27,7 @@ _DT2TORCH = {F16: torch.float16, BF16: torch.bfloat16}
 SYMBOLS = [
     "i2it_default_config", "i2it_create", "i2it_destroy", "i2it_last_error", "i2it_set_weight",
     "i2it_set_adapter_scale", "i2it_finalize_weights", "i2it_workspace_bytes", "i2it_forward",
-    "i2it_launch_count", "i2it_read_stage", "i2it_op_conv2d", "i2it_op_group_norm", "i2it_op_layer_norm",
+    "i2it_launch_count", "i2it_profile", "i2it_read_stage", "i2it_op_conv2d", "i2it_op_group_norm", "i2it_op_layer_norm",
     "i2it_op_attention", "i2it_op_upsample2x",
 ]
 
@@ -68,6 +68,7 @@ def load_library(path: Optional[str] = None):
     lib.i2it_workspace_bytes.argtypes = [vp, ci, ci, ci, C.POINTER(C.c_size_t)]
     lib.i2it_forward.argtypes = [vp, vp, vp, ci, vp, vp, cf, vp, vp, ci, ci, ci, ci, vp]
     lib.i2it_launch_count.argtypes = [vp, ci, ci, ci, ci, C.POINTER(ci)]
+    lib.i2it_profile.argtypes = [vp, ci, C.c_char_p, C.c_size_t, vp]
     lib.i2it_read_stage.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(ci)]
     lib.i2it_op_conv2d.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, vp, ci, ci, vp, ci, ci, vp]
     lib.i2it_op_group_norm.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp, cf, ci, vp, ci, vp]
@@ -180,6 +181,14 @@ class Engine:
         n = C.c_int(0)
         self._check(self.lib.i2it_launch_count(self._h, B, H, W, direction, C.byref(n)), "i2it_launch_count")
         return n.value
+
+    def profile(self, reps: int = 3):
+        """Per-launch timings of the last forward's plan: list of dicts (kind, ms, flops, bytes, shape)."""
+        import json
+        cap = 1 << 22
+        buf = C.create_string_buffer(cap)
+        self._check(self.lib.i2it_profile(self._h, reps, buf, cap, _stream()), "i2it_profile")
+        return json.loads(buf.value.decode())
 
     def workspace_bytes(self, B: int, H: int, W: int) -> int:
         n = C.c_size_t(0)

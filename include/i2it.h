@@ -100,6 +100,11 @@ int i2it_forward(i2it_handle* h, const void* x, const void* text_emb, int text_b
 /* Number of kernel launches one forward of this shape issues (for bench accounting). */
 int i2it_launch_count(i2it_handle* h, int batch, int H, int W, int direction, int* launches);
 
+/* Per-launch device timing of the plan the LAST forward used: runs it `reps` more times with CUDA events around
+ * every launch and writes a JSON array [{"i","kind","ms","flops","bytes","shape"}...] (algorithmic flops/bytes per
+ * launch) into `json`.  Synchronous.  This is what bench.py's roofline numbers are computed from. */
+int i2it_profile(i2it_handle* h, int reps, char* json, size_t cap, void* stream);
+
 /* Named intermediate tensors of the LAST forward (needs cfg.keep_stages): copies the stage as fp32 NCHW
  * into dst (device pointer) and reports its dims.  Synchronous.  Names: "skip0".."skip3", "moments",
  * "latent", "model_pred", "dec_in", "pre_out".... */

@@ -1,0 +1,168 @@
+"""CPU tests of the host side: C-ABI library loads and exports every declared symbol (no compute calls), the mirrors of the
+reference API keep its names / signatures / error behaviour, checkpoint formats round-trip, sharding logic (gloo, world 2)."""
+import inspect
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _text_stack():
+    class Tok:
+        model_max_length = 77
+
+        def __call__(self, text, **kw):
+            from types import SimpleNamespace
+            n = 1 if isinstance(text, str) else len(text)
+            return SimpleNamespace(input_ids=torch.zeros(n, 77, dtype=torch.long))
+    return Tok(), None
+
+
+def test_library_exports_every_declared_symbol():
+    import i2it
+    hdr = open(os.path.join(ROOT, "include", "i2it.h")).read()
+    declared = set(re.findall(r"\b(i2it_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(i2it.SYMBOLS), declared ^ set(i2it.SYMBOLS)
+    lib = i2it.load_library()
+    for s in declared:
+        assert getattr(lib, s) is not None
+    out = subprocess.run(["nm", "-D", "--defined-only", i2it.LIB_PATH], capture_output=True, text=True).stdout
+    for s in declared:
+        assert re.search(rf"\bT {s}\b", out), f"{s} not exported"
+
+
+def test_default_config_matches_sd_turbo():
+    import ctypes as C
+    import i2it
+    import weights as W
+    lib = i2it.load_library()
+    c = i2it.Config()
+    assert lib.i2it_default_config(C.byref(c)) == 0
+    assert tuple(c.unet_channels) == W.SD_TURBO["unet_channels"] and tuple(c.unet_heads) == W.SD_TURBO["unet_heads"]
+    assert tuple(c.vae_channels) == W.SD_TURBO["vae_channels"] and c.cross_dim == 1024 and c.temb_dim == 1280
+    assert abs(c.scaling_factor - 0.18215) < 1e-7
+
+
+def test_no_gpu_fails_loudly():
+    import i2it
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        i2it.Engine(torch.bfloat16)
+
+
+def test_pix2pix_signature_matches_reference():
+    from pix2pix_turbo import Pix2Pix_Turbo, TwinConv
+    sig = inspect.signature(Pix2Pix_Turbo.__init__)
+    names = list(sig.parameters)[1:6]
+    assert names == ["pretrained_name", "pretrained_path", "ckpt_folder", "lora_rank_unet", "lora_rank_vae"]   # ref :30
+    assert [sig.parameters[n].default for n in names] == [None, None, "checkpoints", 8, 4]
+    f = inspect.signature(Pix2Pix_Turbo.forward)
+    assert list(f.parameters)[1:7] == ["c_t", "prompt", "prompt_tokens", "deterministic", "r", "noise_map"]       # ref :186
+    assert f.parameters["deterministic"].default is True and f.parameters["r"].default == 1.0
+    for m in ("set_eval", "set_train", "save_model"):
+        assert hasattr(Pix2Pix_Turbo, m)
+    assert list(inspect.signature(TwinConv.__init__).parameters)[1:] == ["convin_pretrained", "convin_curr"]
+
+
+def test_cyclegan_signature_matches_reference():
+    from cyclegan_turbo import CycleGAN_Turbo, VAE_decode, VAE_encode
+    sig = inspect.signature(CycleGAN_Turbo.__init__)
+    assert list(sig.parameters)[1:6] == ["pretrained_name", "pretrained_path", "ckpt_folder", "lora_rank_unet", "lora_rank_vae"]
+    f = inspect.signature(CycleGAN_Turbo.forward)
+    assert list(f.parameters)[1:5] == ["x_t", "direction", "caption", "caption_emb"]                              # ref :241
+    fw = inspect.signature(CycleGAN_Turbo.forward_with_networks)
+    assert list(fw.parameters)[:8] == ["x", "direction", "vae_enc", "unet", "vae_dec", "sched", "timesteps", "text_emb"]
+    assert hasattr(CycleGAN_Turbo, "get_traininable_params")
+    for cls in (VAE_encode, VAE_decode):
+        assert list(inspect.signature(cls.__init__).parameters)[1:3] == ["vae", "vae_b2a"]
+
+
+def test_pix2pix_host_behaviour(tmp_path):
+    import weights as W
+    from pix2pix_turbo import Pix2Pix_Turbo
+    m = Pix2Pix_Turbo(cfg=W.TINY, text_stack=_text_stack())
+    assert m.timesteps.tolist() == [999] and m.vae.decoder.gamma == 1
+    assert abs(float(m.sched.alphas_cumprod[999]) - 0.0046600951) < 1e-9
+    m.set_eval()
+    assert m.half() is m and m.compute_dtype == torch.float16
+    m.unet.enable_xformers_memory_efficient_attention()                    # must exist (inference_unpaired.py:36)
+    with pytest.raises(AssertionError, match="Either prompt or prompt_tokens"):   # reference :188
+        m(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(AssertionError):
+        m(torch.zeros(1, 3, 64, 64), prompt="a", prompt_tokens=torch.zeros(1, 77, dtype=torch.long))
+    # checkpoint format of save_model (reference :221-229) round-trips through pretrained_path (reference :111-125)
+    p = str(tmp_path / "m.pkl")
+    m.save_model(p)
+    sd = torch.load(p)
+    assert set(sd) == {"unet_lora_target_modules", "vae_lora_target_modules", "rank_unet", "rank_vae", "state_dict_unet",
+                       "state_dict_vae"}
+    assert all(("lora" in k or "conv_in" in k) for k in sd["state_dict_unet"])
+    assert all(("lora" in k or "skip" in k) for k in sd["state_dict_vae"])
+    key = next(k for k in sd["state_dict_unet"] if "lora_B" in k)
+    sd["state_dict_unet"][key] = sd["state_dict_unet"][key] + 1.0
+    torch.save(sd, p)
+    with pytest.warns(UserWarning):
+        m2 = Pix2Pix_Turbo(pretrained_path=p, cfg=W.TINY, text_stack=_text_stack())
+    assert torch.equal(m2.unet.state_dict()[key], sd["state_dict_unet"][key])
+
+
+def test_cyclegan_host_behaviour():
+    import weights as W
+    from cyclegan_turbo import CycleGAN_Turbo
+    m = CycleGAN_Turbo(cfg=W.TINY, text_stack=_text_stack())
+    with pytest.raises(AssertionError):                                    # reference :243: direction must be known
+        m(torch.zeros(1, 3, 64, 64))
+    m.direction, m.caption = "a2b", None
+    with pytest.raises(AssertionError):                                    # reference :246: caption must be known
+        m(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(AssertionError):                                    # reference :202
+        CycleGAN_Turbo.forward_with_networks(torch.zeros(1, 3, 64, 64), "sideways", m.vae_enc, m.unet, m.vae_dec, m.sched,
+                                             m.timesteps, torch.zeros(1, 77, 128))
+    assert m.eval() is m
+    # every UNet LoRA layer belongs to exactly one of the three adapters (cyclegan_turbo.py:53-72)
+    ads = {k.split(".lora_A.")[1].split(".")[0] for k in m._sd if k.startswith("unet.") and ".lora_A." in k}
+    assert ads == {"default_encoder", "default_decoder", "default_others"}
+    assert any(k.startswith("vae_b2a.") for k in m._sd)
+
+
+def test_shard_ranges():
+    from dist import shard_range
+    for B in (1, 7, 8, 64, 128):
+        for world in (1, 2, 3, 8):
+            rs = [shard_range(B, r, world) for r in range(world)]
+            assert rs[0][0] == 0 and rs[-1][1] == B
+            assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
+            assert max(h - l for l, h in rs) - min(h - l for l, h in rs) <= 1
+
+
+def test_sharded_allgather_gloo_world2(tmp_path):
+    # N>1 path on CPU: two gloo ranks shard a batch, run a per-sample "model", all-gather -> identical to unsharded
+    script = tmp_path / "w.py"
+    script.write_text(f"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {os.path.join(ROOT, 'img2img-turbo_b200')!r})
+from dist import sharded_forward
+dist.init_process_group('gloo')
+B = 5
+x = torch.arange(B * 3 * 4 * 4, dtype=torch.float32).view(B, 3, 4, 4)
+eps = torch.arange(B * 2, dtype=torch.float32).view(B, 2)
+model = lambda xs, prompt, eps=None: xs * 2 + eps.view(-1, 1, 1, 1)[:, :, :1, :1]
+y = sharded_forward(model, x, 'p', eps=eps[:, :1])
+ref = x * 2 + eps[:, :1].view(-1, 1, 1, 1)
+assert torch.equal(y, ref), (y - ref).abs().max()
+x8 = torch.randn(8, 3, 2, 2, generator=torch.Generator().manual_seed(0))
+y8 = sharded_forward(lambda xs: xs + 1, x8)
+assert torch.equal(y8, x8 + 1)
+dist.destroy_process_group()
+print('rank', os.environ['RANK'], 'ok')
+""")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2

@@ -1,0 +1,141 @@
+"""CPU tests of the oracle itself: checksums, analytic constants, algebraic known-answer identities, golden vectors.
+(The reference ships no tests or fixtures for this path — SURVEY.md section 4 — so these are what pins the restatement.)"""
+import os
+
+import pytest
+import torch
+
+import oracle as O
+import weights as W
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _inputs(kind, B, H, cfg, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    if kind == "pix2pix":
+        x = (torch.rand(B, 1, H, H, generator=g) < 0.08).float().expand(-1, 3, -1, -1).contiguous()
+    else:
+        x = torch.rand(B, 3, H, H, generator=g) * 2 - 1
+    text = torch.randn(B, 77, cfg["cross_dim"], generator=g)
+    eps = torch.randn(B, 4, H // 8, H // 8, generator=g)
+    noise = torch.randn(B, 4, H // 8, H // 8, generator=g)
+    return x, text, eps, noise
+
+
+def test_param_count_checksums():
+    # the layer enumeration must reproduce the published SD-Turbo parameter counts exactly
+    assert W.param_count(W.unet_specs(W.SD_TURBO)) == 865_910_724
+    assert W.param_count(W.vae_specs(W.SD_TURBO)) == 83_653_863
+    assert sum(a * b for a, b in W.skip_conv_shapes(W.SD_TURBO)) == 491_520
+    assert W.skip_conv_shapes(W.SD_TURBO) == [(512, 512), (256, 512), (128, 512), (128, 256)]
+    n_lora = sum(1 for k, _, _ in W.unet_specs(W.SD_TURBO) if W.unet_adapter_for(k, "pix2pix"))
+    assert n_lora == 257                                   # suffix match => 257 UNet layers
+
+
+def test_scheduler_constants():
+    ac = O.alphas_cumprod()
+    assert abs(float(ac[999]) - 0.0046600951) < 1e-9
+    assert abs(float(ac[999].sqrt()) - 0.06826489) < 1e-7
+    assert abs(float((1 - ac[999]).sqrt()) - 0.99766723) < 1e-7
+    x, e = torch.randn(2, 4, 8, 8), torch.randn(2, 4, 8, 8)
+    x0 = O.ddpm_step_x0(e, x)
+    assert torch.allclose(x0, (x - 0.99766723 * e) / 0.06826489, rtol=1e-5, atol=1e-5)
+
+
+def test_timestep_embedding_layout():
+    te = O.timestep_embedding(999, 320)
+    assert te.shape == (1, 320)
+    assert abs(float(te[0, 0]) - torch.cos(torch.tensor(999.0)).item()) < 1e-6     # flip_sin_to_cos: cos first
+    assert abs(float(te[0, 160]) - torch.sin(torch.tensor(999.0)).item()) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["pix2pix_tiny_det", "pix2pix_tiny_stochastic", "cyclegan_tiny_a2b", "cyclegan_tiny_b2a"])
+def test_golden_vectors(name):
+    gold = torch.load(os.path.join(GOLD, name + ".pt"))
+    cfg = W.TINY
+    with torch.no_grad():
+        st = {}
+        if name.startswith("pix2pix"):
+            x, text, eps, noise = _inputs("pix2pix", 2, 64, cfg)
+            if "stochastic" in name:
+                sd = W.make_state_dict("pix2pix", cfg, seed=0, twin=True, perturb_norm=True)
+                y = O.pix2pix_forward(sd, x, text, eps, cfg, deterministic=False, r=0.4, noise_map=noise, stages=st)
+            else:
+                sd = W.make_state_dict("pix2pix", cfg, seed=0, perturb_norm=True)
+                y = O.pix2pix_forward(sd, x, text, eps, cfg, stages=st)
+        else:
+            sd = W.make_state_dict("cyclegan", cfg, seed=0, perturb_norm=True)
+            x, text, eps, _ = _inputs("cyclegan", 2, 64, cfg)
+            y = O.cyclegan_forward(sd, x, text, eps, name[-3:], cfg, stages=st)
+    assert torch.allclose(st["model_pred"], gold["model_pred"], rtol=1e-3, atol=1e-4)
+    assert torch.allclose(st["x_denoised"], gold["x_denoised"], rtol=1e-3, atol=2e-3)
+    assert (y - gold["image"].float()).abs().max() < 5e-3
+
+
+def test_lora_fold_equals_unfolded(tiny_sd):
+    # known-answer identity behind the product's load-time fold: base(x) + s*B(A(x)) == (W + s*B@A)(x)
+    cfg = W.TINY
+    x, text, eps, _ = _inputs("pix2pix", 1, 64, cfg)
+    scales = {"default": 1.0, "vae_skip": 2.0}
+    folded = {}
+    for k, v in tiny_sd.items():
+        if ".lora_" in k:
+            continue
+        folded[k] = v
+    for k in list(folded):
+        if k.endswith(".weight") and any(kk.startswith(k[:-7] + ".lora_A.") for kk in tiny_sd):
+            folded[k] = O.fold_lora(tiny_sd, k[:-7], scales)
+    with torch.no_grad():
+        a = O.pix2pix_forward(tiny_sd, x, text, eps, cfg)
+        b = O.pix2pix_forward(folded, x, text, eps, cfg)
+    assert (a - b).abs().max() < 2e-3
+
+
+def test_zero_lora_b_is_base_model():
+    cfg = W.TINY
+    sd = W.make_state_dict("pix2pix", cfg, seed=0, lora_b_std=0.0)
+    base = {k: v for k, v in sd.items() if ".lora_" not in k}
+    x, text, eps, _ = _inputs("pix2pix", 1, 64, cfg)
+    with torch.no_grad():
+        a, b = O.pix2pix_forward(sd, x, text, eps, cfg), O.pix2pix_forward(base, x, text, eps, cfg)
+    assert (a - b).abs().max() < 1e-5     # not bit-equal: the zero branch changes CPU kernel scheduling, not the math
+
+
+def test_gamma1_stochastic_equals_deterministic():
+    # r = 1: unet_input = enc, LoRA weight 1, decoder.gamma 1, TwinConv -> conv_in_curr   (src/pix2pix_turbo.py:204-218)
+    cfg = W.TINY
+    sdt = W.make_state_dict("pix2pix", cfg, seed=0, twin=True)
+    sdd = {}
+    for k, v in sdt.items():
+        if "conv_in_pretrained" in k:
+            continue
+        sdd[k.replace("conv_in.conv_in_curr", "conv_in")] = v
+    x, text, eps, noise = _inputs("pix2pix", 1, 64, cfg)
+    with torch.no_grad():
+        a = O.pix2pix_forward(sdt, x, text, eps, cfg, deterministic=False, r=1.0, noise_map=noise)
+        b = O.pix2pix_forward(sdd, x, text, eps, cfg)
+    assert (a - b).abs().max() < 1e-5
+
+
+def test_skip_conv_gamma_is_linear(tiny_sd):
+    a = torch.randn(1, 64, 16, 16)
+    y1 = O.conv2d(tiny_sd, "vae.decoder.skip_conv_4", a * 0.4, {"vae_skip": 2.0})
+    y2 = O.conv2d(tiny_sd, "vae.decoder.skip_conv_4", a, {"vae_skip": 2.0}) * 0.4
+    assert torch.allclose(y1, y2, rtol=1e-5, atol=1e-6)
+
+
+def test_skip_convs_constant_init(tiny_sd):
+    for i in range(1, 5):
+        w = tiny_sd[f"vae.decoder.skip_conv_{i}.weight"]
+        assert torch.all(w == 1e-5)                        # src/pix2pix_turbo.py:133-136
+
+
+def test_batch_independence(tiny_sd):
+    # images never interact (per-sample GN/LN/attention): the property that makes batch sharding exact
+    cfg = W.TINY
+    x, text, eps, _ = _inputs("pix2pix", 2, 64, cfg)
+    with torch.no_grad():
+        full = O.pix2pix_forward(tiny_sd, x, text, eps, cfg)
+        one = O.pix2pix_forward(tiny_sd, x[1:], text[1:], eps[1:], cfg)
+    assert (full[1:] - one).abs().max() < 1e-4
