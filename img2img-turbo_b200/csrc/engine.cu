@@ -2,6 +2,7 @@
 #include "engine.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace i2it {
 
@@ -109,6 +110,9 @@ Engine::Engine(const i2it_config& c) : cfg(c), dtype(c.dtype) {
   num_sms = prop.multiProcessorCount;
   I2IT_CUDA(cudaFuncSetAttribute(tapgemm_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
   I2IT_CUDA(cudaFuncSetAttribute(tapgemm_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+  I2IT_CUDA(cudaFuncSetAttribute(flash_attn_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+  I2IT_CUDA(cudaFuncSetAttribute(flash_attn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+  use_flash = std::getenv("I2IT_NO_FLASH") == nullptr;
   int* h = nullptr;
   I2IT_CUDA(cudaHostAlloc(&h, sizeof(int), cudaHostAllocMapped));
   *h = 0;
@@ -394,7 +398,8 @@ int Engine::pick_bn(long long m_tiles, int N, bool) const {
     if (bn > round_up(N, 16)) continue;
     const long long tiles = m_tiles * ceil_div(N, bn);
     const long long waves = (tiles + num_sms - 1) / num_sms;
-    const double cost = static_cast<double>(waves) * (std::max(bn, 64) + 24);
+    // a tile's time is bounded by its L2->SMEM traffic (A 128 rows + B bn rows per k-step) as much as by the MMA (bn)
+    const double cost = static_cast<double>(waves) * (128 + bn);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
   }
   return best;
@@ -584,7 +589,7 @@ Act Engine::group_norm(Plan& P, const Act& x, const NormW& nw, float eps, bool s
                        reinterpret_cast<const T*>(xp), ximg, ldx, C, HW, cg, pix, d_part)));
   }, "gn_stats", 0, 2.0 * N * HW * C);
   const double inv_count = 1.0 / (static_cast<double>(HW) * cg);
-  add_op(P, [=](cudaStream_t st) { gn_finalize_kernel<<<N, 32, 0, st>>>(d_part, chunks, inv_count, eps, d_stats); }, "gn_final");
+  add_op(P, [=](cudaStream_t st) { gn_finalize_kernel<<<N, 1024, 0, st>>>(d_part, chunks, inv_count, eps, d_stats); }, "gn_final");
   add_op(P, [=](cudaStream_t st) {
     DISPATCH_T(dt, (gn_apply_kernel<T><<<dim3(chunks, N), threads, 0, st>>>(
                        reinterpret_cast<const T*>(xp), ximg, ldx, reinterpret_cast<T*>(yp), yimg, ldy, C, HW, cg, pix,
@@ -681,6 +686,7 @@ Act Engine::vt_proj(Plan& P, const Act& x, int B, int ntok, const PW& wv) {
 
 Act Engine::attention(Plan& P, const Act& q, const Act& k, const Act& vt, int B, int Nq, int Nk, int heads, int d,
                       int kv_batch) {
+  if (d == FA_D && use_flash) return flash_attention(P, q, k, vt, B, Nq, Nk, heads, kv_batch);
   I2IT_CHECK(d % 64 == 0 && (d <= 256 || d % 256 == 0), "attention: head dim must be a multiple of 64");
   I2IT_CHECK(Nk <= 4096, "attention: Nk > 4096 needs the fused kernel");
   I2IT_CHECK(kv_batch == B || kv_batch == 1, "attention: kv batch must be 1 or B");
@@ -779,6 +785,47 @@ Act Engine::attention(Plan& P, const Act& q, const Act& k, const Act& vt, int B,
     launch_gemm(P, ta, tb, p, static_cast<int>(std::min<long long>(m_tiles * p.n_tiles, num_sms)), false, "tapgemm:attn_pv", Nk,
                 2.0 * (1.0 * rows * Nk + 1.0 * B * heads * Nk * d + 1.0 * rows * d));
   }
+  return out;
+}
+
+Act Engine::flash_attention(Plan& P, const Act& q, const Act& k, const Act& vt, int B, int Nq, int Nk, int heads, int kv_batch) {
+  I2IT_CHECK(kv_batch == B || kv_batch == 1, "attention: kv batch must be 1 or B");
+  const int d = FA_D, C = heads * d;
+  Act out = alloc_act(P, B, 1, Nq, C);
+  TmapSpec sq, sk, sv;
+  sq.base = q.p;
+  sq.dim[0] = d; sq.dim[1] = Nq; sq.dim[2] = heads; sq.dim[3] = B;
+  sq.stride[0] = q.ld * 2ull; sq.stride[1] = d * 2ull; sq.stride[2] = 2ull * Nq * q.ld; sq.stride[3] = sq.stride[2];
+  sq.box[0] = 64; sq.box[1] = FA_BM;
+  fill_strides(sq);
+  sk.base = k.p;
+  sk.dim[0] = d; sk.dim[1] = Nk; sk.dim[2] = heads; sk.dim[3] = kv_batch;
+  sk.stride[0] = k.ld * 2ull; sk.stride[1] = d * 2ull; sk.stride[2] = 2ull * Nk * k.ld; sk.stride[3] = sk.stride[2];
+  sk.box[0] = 64; sk.box[1] = FA_BN;
+  fill_strides(sk);
+  const int ldv = vt.ld;
+  sv.base = vt.p;
+  sv.dim[0] = Nk; sv.dim[1] = d; sv.dim[2] = heads; sv.dim[3] = kv_batch;
+  sv.stride[0] = ldv * 2ull; sv.stride[1] = 2ull * d * ldv; sv.stride[2] = 2ull * C * ldv; sv.stride[3] = sv.stride[2];
+  sv.box[0] = FA_BN; sv.box[1] = d;
+  fill_strides(sv);
+  FlashParams fp;
+  std::memset(&fp, 0, sizeof fp);
+  fp.Nq = Nq; fp.Nk = Nk; fp.heads = heads; fp.B = B;
+  fp.q_tiles = ceil_div(Nq, FA_BM);
+  fp.kv_bmul = (kv_batch == B) ? 1 : 0;
+  fp.scale_log2e = (1.0f / sqrtf(static_cast<float>(d))) * 1.4426950408889634f;
+  fp.out = out.p;
+  fp.ldo = out.ld;
+  fp.idesc = make_idesc(dtype, FA_BN);
+  fp.err = d_err;
+  const CUtensorMap tq = encode_tmap(sq, dtype), tk = encode_tmap(sk, dtype), tv = encode_tmap(sv, dtype);
+  const int grid = fp.q_tiles * heads * B, dt = dtype;
+  char shp[96];
+  snprintf(shp, sizeof shp, "B=%d h=%d Nq=%d Nk=%d d=%d", B, heads, Nq, Nk, d);
+  add_op(P, [=](cudaStream_t st) {
+    DISPATCH_T(dt, (flash_attn_kernel<T><<<grid, FA_THREADS, FA_SMEM, st>>>(tq, tk, tv, fp)));
+  }, "flash_attn", 4.0 * B * heads * Nq * Nk * d, 2.0 * (2.0 * B * Nq * C + 2.0 * kv_batch * Nk * C), shp);
   return out;
 }
 

@@ -12,6 +12,7 @@
 #include "../../include/i2it.h"
 #include "kernels.cuh"
 #include "tapgemm.cuh"
+#include "flash.cuh"
 
 namespace i2it {
 
@@ -126,6 +127,8 @@ class Engine {
   // attention core on projected operands; q/k are column slices of token matrices; returns [B*Nq, heads*d]
   Act attention(Plan& P, const Act& q, const Act& k, const Act& vt, int B, int Nq, int Nk, int heads, int d,
                 int kv_batch);
+  Act flash_attention(Plan& P, const Act& q, const Act& k, const Act& vt, int B, int Nq, int Nk, int heads, int kv_batch);
+  bool use_flash = true;
 
   // ---- weights ----
   bool has(const std::string& key) const;

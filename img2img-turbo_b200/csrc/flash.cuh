@@ -1,0 +1,258 @@
+// flash_attn_kernel: fused softmax(Q K^T * scale) V for head_dim 64 (all UNet self/cross attention of the path).
+//
+// Replaces, per attention layer, the three launches  S = QK^T (fp32 logits to HBM) -> softmax -> O = PV  — i.e. what the
+// reference gets from F.scaled_dot_product_attention / xformers FMHA (diffusers AttnProcessor2_0; call sites under
+// /root/reference/src/pix2pix_turbo.py:199 and /root/reference/src/inference_unpaired.py:36).
+//
+// One CTA = one 128-row Q tile of one (batch, head); 192 threads:
+//   warp 4 lane 0 : TMA producer   Q once; (K_j [64 keys x 64], V^T_j [64 d x 64 keys]) through a 3-stage ring
+//   warp 5 lane 0 : MMA issuer     S_j = Q K_j^T (4 x tcgen05.mma M128 N64 K16) -> TMEM S buffer j&1
+//                                  PV_j = P_j V_j  (4 x tcgen05.mma, A = P_j staged in swizzled smem) -> TMEM cols [128,192)
+//                                  QK_{j+1} is issued as soon as the softmax warps have pulled S_j out of TMEM
+//   warps 0..3    : one Q row per thread: online softmax in fp32 (exp2, running max / sum), P_j -> bf16/fp16 smem tile,
+//                   O accumulated in registers  (o = o*alpha + PV_j),  final O / l written once
+// 2 CTAs per SM (80 KB smem, 256 TMEM columns each: S double-buffered + PV) so one CTA's MMAs overlap the other's exponentials.
+#pragma once
+#include "tapgemm.cuh"
+
+namespace i2it {
+
+constexpr int FA_BM = 128, FA_BN = 64, FA_D = 64, FA_STAGES = 3;
+constexpr int FA_Q_BYTES = FA_BM * FA_D * 2;            // 16 KiB
+constexpr int FA_KV_STAGE = 2 * FA_BN * FA_D * 2;       // K 8 KiB + V^T 8 KiB
+constexpr int FA_P_BYTES = FA_BM * FA_BN * 2;           // 16 KiB
+constexpr int FA_SMEM = FA_Q_BYTES + FA_STAGES * FA_KV_STAGE + FA_P_BYTES + 256 + 1024;
+constexpr int FA_THREADS = 192;
+
+struct FlashParams {
+  int Nq, Nk, heads, B, q_tiles, kv_bmul;   // kv_bmul: 1 if K/V are per batch item, 0 if one K/V set is shared (text)
+  float scale_log2e;                        // softmax scale * log2(e)
+  void* out;                                // [B*Nq, ldo] tokens, head h at columns [64h, 64h+64)
+  long long ldo;
+  uint32_t idesc;                           // M=128, N=64 (both GEMMs)
+  int* err;
+};
+
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void sts16(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(FA_THREADS, 2)
+flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmVt, const __grid_constant__ FlashParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base;
+  const uint32_t sKV = base + FA_Q_BYTES;
+  const uint32_t sP = sKV + FA_STAGES * FA_KV_STAGE;
+  const uint32_t bars = sP + FA_P_BYTES;
+  const uint32_t q_full = bars;
+  auto kv_full = [&](int s) { return bars + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return bars + 8u * (1 + FA_STAGES + s); };
+  // S is double-buffered in TMEM; each buffer has its own full/free barrier so no waiter can fall two phases behind
+  const uint32_t s_full0 = bars + 8u * (1 + 2 * FA_STAGES);
+  auto s_full = [&](int u) { return s_full0 + 8u * u; };
+  auto s_free = [&](int u) { return s_full0 + 16u + 8u * u; };
+  const uint32_t p_full = s_full0 + 32, pv_full = s_full0 + 40;
+  const uint32_t tmem_slot = s_full0 + 48;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x % p.q_tiles;
+  const int h = (blockIdx.x / p.q_tiles) % p.heads;
+  const int b = blockIdx.x / (p.q_tiles * p.heads);
+  const int nkv = (p.Nk + FA_BN - 1) / FA_BN;
+
+  if (warp == 4 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < FA_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    for (int u = 0; u < 2; ++u) { mbar_init(s_full(u), 1); mbar_init(s_free(u), 4); }
+    mbar_init(p_full, 4); mbar_init(pv_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmK)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmVt)) : "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(tmem_slot) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  const uint32_t tS0 = tmem_base, tPV = tmem_base + 128;   // S buffers at columns [0,64) and [64,128)
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, FA_Q_BYTES);
+      tma_load_5d(sQ, &tmQ, q_full, 0, qt * FA_BM, h, b, 0);
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j % FA_STAGES;
+        mbar_wait(kv_empty(s), ((j / FA_STAGES) & 1) ^ 1, p.err, 11);
+        mbar_expect_tx(kv_full(s), FA_KV_STAGE);
+        tma_load_5d(sKV + s * FA_KV_STAGE, &tmK, kv_full(s), 0, j * FA_BN, h, b * p.kv_bmul, 0);
+        tma_load_5d(sKV + s * FA_KV_STAGE + FA_BN * FA_D * 2, &tmVt, kv_full(s), j * FA_BN, 0, h, b * p.kv_bmul, 0);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      mbar_wait(q_full, 0, p.err, 12);
+      const uint64_t qdesc = umma_desc_sw128(sQ), pdesc = umma_desc_sw128(sP);
+      auto issue_qk = [&](int j) {
+        const int s = j % FA_STAGES;
+        mbar_wait(kv_full(s), (j / FA_STAGES) & 1, p.err, 13);
+        tc_fence_after();
+        const uint64_t kdesc = umma_desc_sw128(sKV + s * FA_KV_STAGE);
+#pragma unroll
+        for (int k = 0; k < FA_D / 16; ++k)
+          tc_mma_f16(tS0 + 64 * (j & 1), qdesc + 2 * k, kdesc + 2 * k, p.idesc, k > 0 ? 1u : 0u);
+        tc_commit(s_full(j & 1));
+      };
+      issue_qk(0);
+      for (int j = 0; j < nkv; ++j) {
+        if (j + 1 < nkv) {
+          // S buffer (j+1)&1 was last read by softmax iteration j-1: QK_{j+1} overlaps the exponentials of iteration j
+          if (j >= 1) { mbar_wait(s_free((j + 1) & 1), ((j - 1) >> 1) & 1, p.err, 14); tc_fence_after(); }
+          issue_qk(j + 1);
+        }
+        mbar_wait(p_full, j & 1, p.err, 15);        // P_j is in smem (and PV_{j-1} has been consumed)
+        tc_fence_after();
+        const int s = j % FA_STAGES;
+        const uint64_t vdesc = umma_desc_sw128(sKV + s * FA_KV_STAGE + FA_BN * FA_D * 2);
+#pragma unroll
+        for (int k = 0; k < FA_BN / 16; ++k) tc_mma_f16(tPV, pdesc + 2 * k, vdesc + 2 * k, p.idesc, k > 0 ? 1u : 0u);
+        tc_commit(pv_full);
+        tc_commit(kv_empty(s));                     // K_j and V_j are free once everything issued so far retires
+      }
+    }
+  } else {
+    // ---------------- softmax / output warps: thread = Q row ----------------
+    const int row = warp * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    float o[FA_D];
+#pragma unroll
+    for (int i = 0; i < FA_D; ++i) o[i] = 0.f;
+    float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(s_full(j & 1), (j >> 1) & 1, p.err, 16);
+      tc_fence_after();
+      const uint32_t tS = tS0 + 64 * (j & 1);
+      const int kbase = j * FA_BN;
+      const bool ragged = (kbase + FA_BN > p.Nk);
+      // pass 1: row max of the scaled logits
+      float mx = -INFINITY;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t raw[32];
+        tc_ld32(tS + lane_off + half * 32, raw);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float v = __uint_as_float(raw[i]) * p.scale_log2e;
+          if (ragged && kbase + half * 32 + i >= p.Nk) v = -INFINITY;
+          mx = fmaxf(mx, v);
+        }
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = fast_exp2(m - m_new);      // first tile: exp2(-inf) = 0
+      // fold in PV_{j-1} before P_{j-1}'s smem tile is overwritten
+      if (j > 0) {
+        mbar_wait(pv_full, (j - 1) & 1, p.err, 17);
+        tc_fence_after();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t raw[32];
+          tc_ld32(tPV + lane_off + half * 32, raw);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[half * 32 + i] = o[half * 32 + i] * alpha_prev + __uint_as_float(raw[i]);
+        }
+      }
+      // pass 2: p = exp2(s - m_new), row sum, pack to 16-bit, write the swizzled K-major P tile
+      float psum = 0.f;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t raw[32];
+        tc_ld32(tS + lane_off + half * 32, raw);
+        tc_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float v0 = __uint_as_float(raw[2 * i]) * p.scale_log2e, v1 = __uint_as_float(raw[2 * i + 1]) * p.scale_log2e;
+          if (ragged) {
+            if (kbase + half * 32 + 2 * i >= p.Nk) v0 = -INFINITY;
+            if (kbase + half * 32 + 2 * i + 1 >= p.Nk) v1 = -INFINITY;
+          }
+          const float p0 = fast_exp2(v0 - m_new), p1 = fast_exp2(v1 - m_new);
+          pk[i] = Elem<T>::pack(p0, p1);
+          // the sum uses the ROUNDED probabilities (what the PV GEMM will actually multiply), as SDPA does
+          const float2 pr = Elem<T>::unpack(pk[i]);
+          psum += pr.x + pr.y;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {               // 16-byte group g' = half*4+g holds keys 8g'..8g'+7 of this row
+          const int gg = half * 4 + g;
+          sts16(sP + row * 128 + ((gg ^ (row & 7)) << 4), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        }
+      }
+      l = l * alpha + psum;
+      m = m_new;
+      alpha_prev = alpha;
+      // S_j fully consumed -> the MMA warp may overwrite S with QK_{j+1};  P_j visible to the async proxy -> PV_j may start
+      tc_fence_before();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(s_free(j & 1)); mbar_arrive(p_full); }
+    }
+    // last PV
+    mbar_wait(pv_full, (nkv - 1) & 1, p.err, 18);
+    tc_fence_after();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t raw[32];
+      tc_ld32(tPV + lane_off + half * 32, raw);
+      tc_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[half * 32 + i] = o[half * 32 + i] * alpha_prev + __uint_as_float(raw[i]);
+    }
+    const int q = qt * FA_BM + row;
+    if (q < p.Nq) {
+      const float inv = 1.0f / l;
+      T* optr = reinterpret_cast<T*>(p.out) + (static_cast<long long>(b) * p.Nq + q) * p.ldo + h * FA_D;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        uint4 u;
+        u.x = Elem<T>::pack(o[8 * g] * inv, o[8 * g + 1] * inv);
+        u.y = Elem<T>::pack(o[8 * g + 2] * inv, o[8 * g + 3] * inv);
+        u.z = Elem<T>::pack(o[8 * g + 4] * inv, o[8 * g + 5] * inv);
+        u.w = Elem<T>::pack(o[8 * g + 6] * inv, o[8 * g + 7] * inv);
+        st16(optr + 8 * g, u);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+}  // namespace i2it

@@ -24,8 +24,7 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, long long img_stride, i
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   const int p0 = chunk * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
   const T* xb = x + n * img_stride + vx * 8;
-  for (int p = p0 + vy; p < p1; p += rows) {
-    const uint4 u = ld_nc16(xb + static_cast<long long>(p) * ld);
+  auto acc = [&](const uint4& u) {
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -33,7 +32,16 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, long long img_stride, i
       s[2 * i] += f.x; q[2 * i] += f.x * f.x;
       s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
     }
+  };
+  int p = p0 + vy;
+  for (; p + 3 * rows < p1; p += 4 * rows) {           // 4 independent 16-byte loads in flight per thread
+    const uint4 u0 = ld_nc16(xb + static_cast<long long>(p) * ld);
+    const uint4 u1 = ld_nc16(xb + static_cast<long long>(p + rows) * ld);
+    const uint4 u2 = ld_nc16(xb + static_cast<long long>(p + 2 * rows) * ld);
+    const uint4 u3 = ld_nc16(xb + static_cast<long long>(p + 3 * rows) * ld);
+    acc(u0); acc(u1); acc(u2); acc(u3);
   }
+  for (; p < p1; p += rows) acc(ld_nc16(xb + static_cast<long long>(p) * ld));
   float* mine = s_acc + static_cast<size_t>(vy) * 2 * C;
 #pragma unroll
   for (int i = 0; i < 8; ++i) { mine[vx * 8 + i] = s[i]; mine[C + vx * 8 + i] = q[i]; }
@@ -51,18 +59,26 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, long long img_stride, i
 }
 
 static __global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, double inv_count, float eps,
-                                   float* __restrict__ stats /*[N][32][2] = mean, rstd*/) {
-  const int n = blockIdx.x, g = threadIdx.x;
+                                          float* __restrict__ stats /*[N][32][2] = mean, rstd*/) {
+  // block = 1024 threads: warp g reduces group g over the chunks (fixed lane-strided order + butterfly: reproducible)
+  const int n = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double a = 0.0, b = 0.0;
-  for (int c = 0; c < chunks; ++c) {
+  for (int c = lane; c < chunks; c += 32) {
     const float* o = partial + ((static_cast<long long>(n) * chunks + c) * 32 + g) * 2;
     a += o[0]; b += o[1];
   }
-  const double mean = a * inv_count;
-  double var = b * inv_count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  stats[(n * 32 + g) * 2] = static_cast<float>(mean);
-  stats[(n * 32 + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) {
+    const double mean = a * inv_count;
+    double var = b * inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[(n * 32 + g) * 2] = static_cast<float>(mean);
+    stats[(n * 32 + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
 }
 
 template <typename T>
@@ -84,8 +100,7 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, long long ximg, int ldx
   const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
   const T* xb = x + n * ximg + vx * 8;
   T* yb = y + n * yimg + vx * 8;
-  for (int p = p0 + vy; p < p1; p += rows) {
-    const uint4 u = ld_nc16(xb + static_cast<long long>(p) * ldx);
+  auto xf = [&](const uint4& u) {
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
     uint32_t o[4];
 #pragma unroll
@@ -95,8 +110,20 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, long long ximg, int ldx
       if (silu) { a = silu_f(a); b = silu_f(b); }
       o[i] = Elem<T>::pack(a, b);
     }
-    st16(yb + static_cast<long long>(p) * ldy, make_uint4(o[0], o[1], o[2], o[3]));
+    return make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  int p = p0 + vy;
+  for (; p + 3 * rows < p1; p += 4 * rows) {
+    const uint4 u0 = ld_nc16(xb + static_cast<long long>(p) * ldx);
+    const uint4 u1 = ld_nc16(xb + static_cast<long long>(p + rows) * ldx);
+    const uint4 u2 = ld_nc16(xb + static_cast<long long>(p + 2 * rows) * ldx);
+    const uint4 u3 = ld_nc16(xb + static_cast<long long>(p + 3 * rows) * ldx);
+    st16(yb + static_cast<long long>(p) * ldy, xf(u0));
+    st16(yb + static_cast<long long>(p + rows) * ldy, xf(u1));
+    st16(yb + static_cast<long long>(p + 2 * rows) * ldy, xf(u2));
+    st16(yb + static_cast<long long>(p + 3 * rows) * ldy, xf(u3));
   }
+  for (; p < p1; p += rows) st16(yb + static_cast<long long>(p) * ldy, xf(ld_nc16(xb + static_cast<long long>(p) * ldx)));
 }
 
 // =============================================================================================

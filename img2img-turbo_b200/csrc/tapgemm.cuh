@@ -29,7 +29,8 @@ constexpr int TG_MAX_TAPS = 16;
 constexpr int TG_A_STAGE = TG_BM * TG_BK * 2;    // 16 KiB
 constexpr int TG_B_STAGE = 256 * TG_BK * 2;      // 32 KiB (BN <= 256)
 constexpr int TG_BAR_BYTES = 256;
-constexpr int TG_SMEM = TG_STAGES * (TG_A_STAGE + TG_B_STAGE) + TG_BAR_BYTES + 1024;  // +1024: manual alignment
+constexpr int TG_BIAS_BYTES = 2 * 256 * 4;       // per-tile bias slice, double-buffered like the accumulators
+constexpr int TG_SMEM = TG_STAGES * (TG_A_STAGE + TG_B_STAGE) + TG_BAR_BYTES + TG_BIAS_BYTES + 1024;  // +1024: manual alignment
 constexpr int TG_THREADS = 192;
 constexpr int TG_ACC_COLS = 256;       // TMEM columns per accumulator stage
 
@@ -165,6 +166,89 @@ __device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int til
   return c;
 }
 
+// One 16-column chunk of one accumulator row: alpha, bias, (GEGLU), residual, clamp, single rounding, store.
+template <typename T>
+__device__ __forceinline__ void epilogue_chunk(const TapGemmParams& p, const uint32_t (&raw)[16], int col0, long long obase,
+                                               long long rbase, float rbias, const float* sbias, bool rfast, const uint4& r0,
+                                               const uint4& r1) {
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
+  if (p.bias_mode == TG_BIAS_COL) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += sbias[i];   // smem broadcast; columns >= N hold 0 (staged once per tile)
+  } else if (p.bias_mode == TG_BIAS_ROW) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += rbias;
+  }
+  const bool full = (col0 + 16 <= p.N);
+  if (p.act == TG_ACT_GEGLU) {
+    // interleaved columns (2j, 2j+1) = (h_j, gate_j) -> out column j = h * gelu(gate)
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = v[2 * i] * gelu_erf_f(v[2 * i + 1]);
+    T* optr = reinterpret_cast<T*>(p.out) + obase + (col0 >> 1);
+    if (p.res) {
+      const T* rptr = reinterpret_cast<const T*>(p.res) + rbase + (col0 >> 1);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += Elem<T>::to_f(rptr[i]);
+    }
+    if (full && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0)) {
+      uint4 u;
+      u.x = Elem<T>::pack(o[0], o[1]); u.y = Elem<T>::pack(o[2], o[3]);
+      u.z = Elem<T>::pack(o[4], o[5]); u.w = Elem<T>::pack(o[6], o[7]);
+      st16(optr, u);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (col0 + 2 * i + 1 < p.N) optr[i] = Elem<T>::from_f(o[i]);
+    }
+    return;
+  }
+  if (p.res) {
+    if (rfast) {
+      const uint32_t ru[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 f = Elem<T>::unpack(ru[i]);
+        v[2 * i] += f.x; v[2 * i + 1] += f.y;
+      }
+    } else {
+      const T* rptr = reinterpret_cast<const T*>(p.res) + rbase + col0 * p.rcol;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (col0 + i < p.N) v[i] += Elem<T>::to_f(rptr[i * p.rcol]);
+    }
+  }
+  if (p.act == TG_ACT_CLAMP1) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fminf(fmaxf(v[i], -1.0f), 1.0f);
+  }
+  if (p.out_fp32) {
+    float* optr = reinterpret_cast<float*>(p.out) + obase + col0 * p.ocol;
+    if (full && p.ocol == 1 && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0)) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(optr + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (col0 + i < p.N) optr[i * p.ocol] = v[i];
+    }
+  } else {
+    T* optr = reinterpret_cast<T*>(p.out) + obase + col0 * p.ocol;
+    if (full && p.ocol == 1 && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0)) {
+      uint4 u0, u1;
+      u0.x = Elem<T>::pack(v[0], v[1]);   u0.y = Elem<T>::pack(v[2], v[3]);
+      u0.z = Elem<T>::pack(v[4], v[5]);   u0.w = Elem<T>::pack(v[6], v[7]);
+      u1.x = Elem<T>::pack(v[8], v[9]);   u1.y = Elem<T>::pack(v[10], v[11]);
+      u1.z = Elem<T>::pack(v[12], v[13]); u1.w = Elem<T>::pack(v[14], v[15]);
+      st16(optr, u0);
+      st16(optr + 8, u1);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (col0 + i < p.N) optr[i * p.ocol] = Elem<T>::from_f(v[i]);
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -179,6 +263,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * TG_STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * TG_STAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * TG_STAGES + 4);
+  float* const s_bias = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + TG_BAR_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.n_tiles * p.tdim[0] * p.tdim[1] * p.tdim[2] * p.tdim[3];
@@ -268,93 +353,44 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const float rbias = (p.bias_mode == TG_BIAS_ROW && row_ok) ? p.bias[g1] : 0.0f;
       const int n0 = c.nt * p.BN;
 
+      // stage this tile's bias slice in smem once (a per-chunk global load here stalled the whole epilogue: r01 ncu)
+      float* sb = s_bias + acc * 256;
+      if (p.bias_mode == TG_BIAS_COL) {
+        for (int cc = row; cc < p.BN; cc += 128) sb[cc] = (n0 + cc < p.N) ? p.bias[n0 + cc] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+
       mbar_wait(tfull_bar(acc), aphase, p.err, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * TG_ACC_COLS;
 
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t raw[16];
+      // 64 columns per round: the residual prefetch and four TMEM loads are all in flight before anything is consumed
+      for (int c0 = 0; c0 < p.BN; c0 += 64) {
+        const int nch = min(4, (p.BN - c0) >> 4);
+        const int colg = n0 + c0;
+        // residual fast path: contiguous, 16-byte aligned, whole group inside N
+        uint4 rq[8];
+        const T* rgrp = p.res ? reinterpret_cast<const T*>(p.res) + rbase + colg : nullptr;
+        const bool rfast = p.res && row_ok && p.rcol == 1 && p.act != TG_ACT_GEGLU && (colg + 16 * nch <= p.N) &&
+                           ((reinterpret_cast<uintptr_t>(rgrp) & 15) == 0);
+        if (rfast) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < nch) { rq[2 * j] = ld_nc16(rgrp + 16 * j); rq[2 * j + 1] = ld_nc16(rgrp + 16 * j + 8); }
+        }
+        uint32_t raw[4][16];
         __syncwarp();                                // tcgen05.ld is .sync.aligned: reconverge after the guarded stores
-        tc_ld16(taddr + c0, raw);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < nch) tc_ld16(taddr + c0 + 16 * j, raw[j]);
         tc_wait_ld();
-        const int col0 = n0 + c0;
-        if (!row_ok || col0 >= p.N) continue;
-        float v[16];
+        if (!row_ok) continue;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
-        if (p.bias_mode == TG_BIAS_COL) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) if (col0 + i < p.N) v[i] += p.bias[col0 + i];
-        } else if (p.bias_mode == TG_BIAS_ROW) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += rbias;
-        }
-        const bool full = (col0 + 16 <= p.N);
-        if (p.act == TG_ACT_GEGLU) {
-          // interleaved columns (2j, 2j+1) = (h_j, gate_j) -> out column j = h * gelu(gate)
-          float o[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = v[2 * i] * gelu_erf_f(v[2 * i + 1]);
-          T* optr = reinterpret_cast<T*>(p.out) + obase + (col0 >> 1);
-          if (p.res) {
-            const T* rptr = reinterpret_cast<const T*>(p.res) + rbase + (col0 >> 1);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] += Elem<T>::to_f(rptr[i]);
-          }
-          if (full && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0)) {
-            uint4 u;
-            u.x = Elem<T>::pack(o[0], o[1]); u.y = Elem<T>::pack(o[2], o[3]);
-            u.z = Elem<T>::pack(o[4], o[5]); u.w = Elem<T>::pack(o[6], o[7]);
-            st16(optr, u);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) if (col0 + 2 * i + 1 < p.N) optr[i] = Elem<T>::from_f(o[i]);
-          }
-          continue;
-        }
-        if (p.res) {
-          const T* rptr = reinterpret_cast<const T*>(p.res) + rbase + col0 * p.rcol;
-          if (full && p.rcol == 1 && ((reinterpret_cast<uintptr_t>(rptr) & 15) == 0)) {
-            const uint4 r0 = ld_nc16(rptr), r1 = ld_nc16(rptr + 8);
-            const uint32_t ru[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float2 f = Elem<T>::unpack(ru[i]);
-              v[2 * i] += f.x; v[2 * i + 1] += f.y;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) if (col0 + i < p.N) v[i] += Elem<T>::to_f(rptr[i * p.rcol]);
-          }
-        }
-        if (p.act == TG_ACT_CLAMP1) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fminf(fmaxf(v[i], -1.0f), 1.0f);
-        }
-        if (p.out_fp32) {
-          float* optr = reinterpret_cast<float*>(p.out) + obase + col0 * p.ocol;
-          if (full && p.ocol == 1 && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0)) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              *reinterpret_cast<float4*>(optr + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) if (col0 + i < p.N) optr[i * p.ocol] = v[i];
-          }
-        } else {
-          T* optr = reinterpret_cast<T*>(p.out) + obase + col0 * p.ocol;
-          if (full && p.ocol == 1 && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0)) {
-            uint4 u0, u1;
-            u0.x = Elem<T>::pack(v[0], v[1]);   u0.y = Elem<T>::pack(v[2], v[3]);
-            u0.z = Elem<T>::pack(v[4], v[5]);   u0.w = Elem<T>::pack(v[6], v[7]);
-            u1.x = Elem<T>::pack(v[8], v[9]);   u1.y = Elem<T>::pack(v[10], v[11]);
-            u1.z = Elem<T>::pack(v[12], v[13]); u1.w = Elem<T>::pack(v[14], v[15]);
-            st16(optr, u0);
-            st16(optr + 8, u1);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) if (col0 + i < p.N) optr[i * p.ocol] = Elem<T>::from_f(v[i]);
-          }
+        for (int j = 0; j < 4; ++j) {
+          if (j >= nch) continue;
+          const int col0 = colg + 16 * j;
+          if (col0 >= p.N) continue;
+          epilogue_chunk<T>(p, raw[j], col0, obase, rbase, rbias, sb + c0 + 16 * j, rfast, rq[2 * j], rq[2 * j + 1]);
         }
       }
       tc_fence_before();

@@ -161,6 +161,9 @@ CASES = {
     "attn_cross": lambda: case_attn(hf, 2, 256, 77, 5, 64, kvb=1),
     "attn_4096": lambda: case_attn(bf, 1, 4096, 4096, 2, 64),
     "attn_vae": lambda: case_attn(bf, 1, 1024, 1024, 1, 512),
+    "attn_small": lambda: case_attn(hf, 3, 64, 64, 20, 64),
+    "attn_ragged": lambda: case_attn(bf, 2, 200, 150, 2, 64),
+    "attn_1024": lambda: case_attn(hf, 2, 1024, 1024, 10, 64),
     "upsample": lambda: case_up(bf),
 }
 
