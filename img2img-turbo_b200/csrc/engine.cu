@@ -405,18 +405,23 @@ int Engine::pick_bn(long long m_tiles, int N, bool) const {
   return best;
 }
 
-void Engine::launch_gemm(Plan& P, const CUtensorMap& ta, const CUtensorMap& tb, const TapGemmParams& p, int grid,
-                         bool out_from_io, const char* kind, double k_valid, double bytes) {
+void Engine::launch_gemm(Plan& P, const CUtensorMap& ta, const CUtensorMap& tb, const TapGemmParams& p_in, int grid,
+                         bool out_from_io, const char* kind, double k_valid, double bytes, const CUtensorMap* ta2p,
+                         const CUtensorMap* tb2p) {
+  TapGemmParams p = p_in;
+  for (int t = 0; t < p.num_taps; ++t)
+    if (p.tap_kc[t] == 0) p.tap_kc[t] = p.kchunks;          // single-source callers only set kchunks
+  const CUtensorMap ta2 = ta2p ? *ta2p : ta, tb2 = tb2p ? *tb2p : tb;
   const int dt = dtype;
   Plan* plan = &P;
   const double m_valid = 1.0 * p.ext[0] * p.ext[1] * p.ext[2] * p.ext[3];
   char shp[160];
   snprintf(shp, sizeof shp, "M=%.0f N=%d K=%.0f taps=%d BN=%d tiles=%d grid=%d", m_valid, p.N, k_valid, p.num_taps, p.BN,
            p.n_tiles * p.tdim[0] * p.tdim[1] * p.tdim[2] * p.tdim[3], grid);
-  add_op(P, [ta, tb, p, grid, dt, out_from_io, plan](cudaStream_t st) {
+  add_op(P, [ta, tb, ta2, tb2, p, grid, dt, out_from_io, plan](cudaStream_t st) {
     TapGemmParams q = p;
     if (out_from_io) q.out = plan->io.out;
-    DISPATCH_T(dt, (tapgemm_kernel<T><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, q)));
+    DISPATCH_T(dt, (tapgemm_kernel<T><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, ta2, tb2, q)));
   }, kind, 2.0 * m_valid * p.N * k_valid, bytes, shp);
 }
 
@@ -544,13 +549,44 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o) {
   p.err = d_err;
 
   const CUtensorMap ta = encode_tmap(sa, dtype), tb = encode_tmap(sb, dtype);
+  CUtensorMap ta2 = ta, tb2 = tb;
+  double k2 = 0;
+  if (o.x2) {
+    // extra 1x1 "tap" over a second activation tensor with the same spatial geometry as the output
+    I2IT_CHECK(o.w2 && o.stride == 1 && o.w2->taps == 1 && o.w2->rows == w.rows, "conv: bad second source");
+    I2IT_CHECK(o.x2->N == x.N && o.x2->H == Ho && o.x2->W == Wo && (o.x2->C == o.w2->cin || o.x2->C == o.w2->cin_pad),
+               "conv: second source shape mismatch");
+    I2IT_CHECK(taps + 1 <= TG_MAX_TAPS, "conv: too many taps");
+    TmapSpec sa2 = sa, sb2;
+    sa2.base = o.x2->p;
+    sa2.dim[0] = o.x2->C;
+    sa2.stride[0] = o.x2->ld * 2ull; sa2.stride[1] = 2ull * o.x2->W * o.x2->ld; sa2.stride[2] = 2ull * o.x2->H * o.x2->W * o.x2->ld;
+    sa2.stride[3] = sa2.stride[2];
+    fill_strides(sa2);
+    sb2.base = o.w2->w;
+    sb2.dim[0] = o.w2->cin_pad; sb2.dim[1] = o.w2->rows;
+    sb2.stride[0] = o.w2->cin_pad * 2ull; sb2.stride[1] = 2ull * o.w2->rows * o.w2->cin_pad; sb2.stride[2] = sb2.stride[1];
+    sb2.stride[3] = sb2.stride[1];
+    sb2.box[0] = 64; sb2.box[1] = p.BN;
+    fill_strides(sb2);
+    ta2 = encode_tmap(sa2, dtype);
+    tb2 = encode_tmap(sb2, dtype);
+    for (int t = 0; t < taps; ++t) { p.tap_src[t] = 0; p.tap_kc[t] = p.kchunks; }
+    const int t2 = taps;
+    for (int d = 0; d < 5; ++d) p.tap_a[t2][d] = 0;
+    for (int d = 0; d < 4; ++d) p.tap_b[t2][d] = 0;
+    p.tap_src[t2] = 1;
+    p.tap_kc[t2] = ceil_div(o.x2->C, 64);
+    p.num_taps = taps + 1;
+    k2 = o.w2->cin;
+  }
   const int grid = static_cast<int>(std::min<long long>(m_tiles * p.n_tiles, num_sms));
   {
-    const double m_valid = 1.0 * x.N * Ho * Wo, k_valid = 1.0 * taps * w.cin;
+    const double m_valid = 1.0 * x.N * Ho * Wo, k_valid = 1.0 * taps * w.cin + k2;
     const double bytes = 2.0 * (1.0 * x.N * x.H * x.W * w.cin + m_valid * outc * (o.out_fp32 ? 2 : 1) + 1.0 * gemm_n * k_valid +
-                                (o.res ? m_valid * outc : 0));
+                                (o.res ? m_valid * outc : 0) + m_valid * k2);
     const char* kind = (k == 3) ? (o.stride == 2 ? "tapgemm:conv3x3s2" : "tapgemm:conv3x3") : "tapgemm:linear";
-    launch_gemm(P, ta, tb, p, grid, o.to_io_out_nchw, kind, k_valid, bytes);
+    launch_gemm(P, ta, tb, p, grid, o.to_io_out_nchw, kind, k_valid, bytes, &ta2, &tb2);
   }
   return out;
 }

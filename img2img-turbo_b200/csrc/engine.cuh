@@ -90,6 +90,9 @@ struct ConvOpts {
   float alpha = 1.f;
   bool to_io_out_nchw = false;   // final image: write NCHW straight into IO.out
   int bias_mode = -1;            // -1: column bias iff the weight has one
+  // second source folded into the same accumulator: out = conv(x) + conv1x1(x2)   (resnet conv_shortcut, decoder skip convs)
+  const Act* x2 = nullptr;
+  const PW* w2 = nullptr;
 };
 
 struct WT {                      // raw fp32 tensor of the state dict, on device
@@ -144,7 +147,7 @@ class Engine {
   Act build_vae_encoder(Plan& P, const std::string& vp, int B, int H, int W, std::vector<Act>& skips);
   Act build_unet(Plan& P, const Act& z, int text_batch);
   void build_vae_decoder(Plan& P, const std::string& vp, const Act& dec_in, std::vector<Act>& skips);
-  Act vae_resnet(Plan& P, const std::string& p, const Act& x);
+  Act vae_resnet(Plan& P, const std::string& p, const Act& x, const Act* skip = nullptr, const PW* skip_w = nullptr);
   Act vae_attn(Plan& P, const std::string& p, const Act& x);
   Act unet_resnet(Plan& P, const std::string& p, const Act& x);
   Act unet_xformer(Plan& P, const std::string& p, const Act& x, int heads, int text_batch);
@@ -157,7 +160,8 @@ class Engine {
     P.meta.push_back(m);
   }
   void launch_gemm(Plan& P, const CUtensorMap& ta, const CUtensorMap& tb, const TapGemmParams& p, int grid,
-                   bool out_from_io, const char* kind, double k_valid, double bytes);
+                   bool out_from_io, const char* kind, double k_valid, double bytes, const CUtensorMap* ta2 = nullptr,
+                   const CUtensorMap* tb2 = nullptr);
   std::string profile_json(int reps, cudaStream_t st);
   int pick_bn(long long m_tiles, int N, bool even32) const;
 

@@ -20,16 +20,22 @@ static inline int ceil_div_i(long long a, long long b) { return static_cast<int>
   } while (0)
 
 // ------------------------------------------------------------------------------------------ VAE
-Act Engine::vae_resnet(Plan& P, const std::string& p, const Act& x) {
+Act Engine::vae_resnet(Plan& P, const std::string& p, const Act& x, const Act* skip, const PW* skip_w) {
   Act h = group_norm(P, x, norm(p + ".norm1"), 1e-6f, true);
   h = conv(P, h, prep(p + ".conv1", {p + ".conv1"}), ConvOpts());
   h = group_norm(P, h, norm(p + ".norm2"), 1e-6f, true);
-  Act sc = x;
+  ConvOpts o;
   if (has(p + ".conv_shortcut.weight")) {
-    ConvOpts o1; o1.ksize = 1;
-    sc = conv(P, x, prep(p + ".conv_shortcut", {p + ".conv_shortcut"}), o1);
+    // x + conv2(h) with a 1x1 shortcut: the shortcut is one more K-slab of the SAME GEMM (second A tensor), its bias is
+    // pre-added to conv2's, so there is no separate launch and no residual read
+    I2IT_CHECK(skip == nullptr, "vae_resnet: shortcut and skip source at once");
+    PW wsc = prep(p + ".conv_shortcut", {p + ".conv_shortcut"});
+    PW w2 = prep(p + ".conv2+sc", {p + ".conv2"}, false, 1.f, raw(p + ".conv_shortcut", "bias").d);
+    o.x2 = &x; o.w2 = &wsc;
+    return conv(P, h, w2, o);
   }
-  ConvOpts o; o.res = &sc;
+  o.res = &x;
+  if (skip) { o.x2 = skip; o.w2 = skip_w; }        // decoder: the next block's  + skip_conv(skip*gamma)  folded in here
   return conv(P, h, prep(p + ".conv2", {p + ".conv2"}), o);
 }
 
@@ -101,23 +107,27 @@ void Engine::build_vae_decoder(Plan& P, const std::string& vp, const Act& dec_in
   ConvOpts o1; o1.ksize = 1;
   Act s = conv(P, dec_in, prep(vp + "post_quant_conv", {vp + "post_quant_conv"}), o1);
   s = conv(P, s, prep(d + ".conv_in", {d + ".conv_in"}), ConvOpts());
+  // `sample = sample + skip_conv_i(skip_i * gamma)` (src/model.py:40-42) is folded into whichever conv PRODUCES `sample`
+  // for up-block i: mid_block.resnets.1.conv2 for i = 0, the previous block's upsampler conv for i >= 1.  gamma is folded
+  // into the bias-free 1x1 weights.
+  auto skip_w = [&](int i) { const std::string sk = d + ".skip_conv_" + std::to_string(i + 1); return prep(sk, {sk}, false, skip_gamma_); };
   s = vae_resnet(P, d + ".mid_block.resnets.0", s);
   s = vae_attn(P, d + ".mid_block.attentions.0", s);
-  s = vae_resnet(P, d + ".mid_block.resnets.1", s);
+  {
+    PW w0 = skip_w(0);
+    s = vae_resnet(P, d + ".mid_block.resnets.1", s, &skips[3], &w0);
+    skips[3] = Act();
+  }
   mark(P, "dec_mid", s);
   for (int i = 0; i < 4; ++i) {
-    // sample = sample + skip_conv_i(skip * gamma): gamma folded into the (bias-free) 1x1 weights, add fused as residual
-    const std::string sk = d + ".skip_conv_" + std::to_string(i + 1);
-    ConvOpts os; os.ksize = 1; os.res = &s;
-    Act skip = skips[3 - i];
-    Act s2 = conv(P, skip, prep(sk, {sk}, false, skip_gamma_), os);
-    skips[3 - i] = Act();                                 // last use: let the pool reclaim it
-    s = s2;
     for (int j = 0; j < 3; ++j) s = vae_resnet(P, d + ".up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), s);
     if (i < 3) {
       s = upsample2x(P, s);
       const std::string u = d + ".up_blocks." + std::to_string(i) + ".upsamplers.0.conv";
-      s = conv(P, s, prep(u, {u}), ConvOpts());
+      PW wn = skip_w(i + 1);
+      ConvOpts ou; ou.x2 = &skips[2 - i]; ou.w2 = &wn;
+      s = conv(P, s, prep(u, {u}), ou);
+      skips[2 - i] = Act();
     }
     mark(P, "dec_up" + std::to_string(i), s);
   }
@@ -132,12 +142,14 @@ Act Engine::unet_resnet(Plan& P, const std::string& p, const Act& x) {
   // t == 999 always: time_emb_proj(silu(emb)) is a per-channel constant -> part of conv1's bias
   h = conv(P, h, prep(p + ".conv1", {p + ".conv1"}, false, 1.f, temb_bias(p)), ConvOpts());
   h = group_norm(P, h, norm(p + ".norm2"), 1e-5f, true);
-  Act sc = x;
+  ConvOpts o;
   if (has(p + ".conv_shortcut.weight")) {
-    ConvOpts o1; o1.ksize = 1;
-    sc = conv(P, x, prep(p + ".conv_shortcut", {p + ".conv_shortcut"}), o1);
+    PW wsc = prep(p + ".conv_shortcut", {p + ".conv_shortcut"});
+    PW w2 = prep(p + ".conv2+sc", {p + ".conv2"}, false, 1.f, raw(p + ".conv_shortcut", "bias").d);
+    o.x2 = &x; o.w2 = &wsc;
+    return conv(P, h, w2, o);
   }
-  ConvOpts o; o.res = &sc;
+  o.res = &x;
   return conv(P, h, prep(p + ".conv2", {p + ".conv2"}), o);
 }
 

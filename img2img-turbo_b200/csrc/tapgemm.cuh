@@ -45,7 +45,9 @@ struct TapGemmParams {
   int a_mul[4];    // A coordinate(d) = t_d * a_mul[d] + tap_a[tap][d+1]
   int b_mul[3];    // B coordinate(2..4) = t_{2..4} * b_mul + tap_b[tap][1..3]
   int n_tiles, BN, N;
-  int num_taps, kchunks;
+  int num_taps, kchunks;   // kchunks: default K chunks per tap (tap_kc overrides per tap)
+  int tap_src[TG_MAX_TAPS]; // 0: (tmA, tmB)   1: (tmA2, tmB2) — a second activation tensor folded into the same accumulator
+  int tap_kc[TG_MAX_TAPS];  // K chunks (of 64) for this tap
   int tap_a[TG_MAX_TAPS][5];
   int tap_b[TG_MAX_TAPS][4];
   uint32_t idesc;
@@ -252,6 +254,7 @@ __device__ __forceinline__ void epilogue_chunk(const TapGemmParams& p, const uin
 template <typename T>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                const __grid_constant__ TapGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -267,7 +270,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.n_tiles * p.tdim[0] * p.tdim[1] * p.tdim[2] * p.tdim[3];
-  const int steps = p.num_taps * p.kchunks;
+  int steps = 0;
+  for (int t = 0; t < p.num_taps; ++t) steps += p.tap_kc[t];
 
   if (warp == 4 && lane == 0) {
     for (int s = 0; s < TG_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -275,6 +279,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA2)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB2)) : "memory");
   }
   if (warp == 5) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
@@ -298,12 +304,15 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int b2 = c.t[1] * p.b_mul[0], b3 = c.t[2] * p.b_mul[1], b4 = c.t[3] * p.b_mul[2];
         const int n0 = c.nt * p.BN;
         for (int t = 0; t < p.num_taps; ++t) {
-          for (int kc = 0; kc < p.kchunks; ++kc) {
+          const CUtensorMap* ta = p.tap_src[t] ? &tmA2 : &tmA;
+          const CUtensorMap* tb = p.tap_src[t] ? &tmB2 : &tmB;
+          const int nkc = p.tap_kc[t];
+          for (int kc = 0; kc < nkc; ++kc) {
             mbar_wait(empty_bar(stage), phase ^ 1, p.err, 1);
             mbar_expect_tx(full_bar(stage), tx_bytes);
-            tma_load_5d(sA + stage * TG_A_STAGE, &tmA, full_bar(stage), kc * TG_BK + p.tap_a[t][0],
+            tma_load_5d(sA + stage * TG_A_STAGE, ta, full_bar(stage), kc * TG_BK + p.tap_a[t][0],
                         a1 + p.tap_a[t][1], a2 + p.tap_a[t][2], a3 + p.tap_a[t][3], a4 + p.tap_a[t][4]);
-            tma_load_5d(sB + stage * TG_B_STAGE, &tmB, full_bar(stage), kc * TG_BK + p.tap_b[t][0], n0,
+            tma_load_5d(sB + stage * TG_B_STAGE, tb, full_bar(stage), kc * TG_BK + p.tap_b[t][0], n0,
                         b2 + p.tap_b[t][1], b3 + p.tap_b[t][2], b4 + p.tap_b[t][3]);
             if (++stage == TG_STAGES) { stage = 0; phase ^= 1; }
           }
