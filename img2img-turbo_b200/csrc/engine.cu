@@ -317,6 +317,26 @@ PW Engine::prep_twin(const std::string& pre, const std::string& cur, float r) {
   return pw;
 }
 
+PW Engine::prep_im2col3(const std::string& name) {
+  const std::string key = name + "|im2col";
+  auto it = prepared_.find(key);
+  if (it != prepared_.end()) return it->second;
+  const WT& w0 = raw(name, "weight");
+  I2IT_CHECK(w0.shape.size() == 4 && w0.shape[1] == 3 && w0.shape[2] == 3 && w0.shape[3] == 3, "prep_im2col3: expects [Cout,3,3,3]");
+  PW pw;
+  pw.rows = static_cast<int>(w0.shape[0]); pw.cin = 32; pw.cin_pad = 32; pw.taps = 1;
+  pw.w = static_cast<uint16_t*>(dmalloc(static_cast<size_t>(pw.rows) * 32 * 2));
+  pw.bias = static_cast<float*>(dmalloc(pw.rows * sizeof(float)));
+  long long numel = 0;
+  float* acc = fold_f32(name, &numel);
+  DISPATCH_T(dtype, (wprep_store_im2col_kernel<T><<<ceil_div(pw.rows * 32, 256), 256>>>(acc, reinterpret_cast<T*>(pw.w), pw.rows)));
+  I2IT_CUDA(cudaMemset(pw.bias, 0, pw.rows * sizeof(float)));
+  bias_store_kernel<<<ceil_div(pw.rows, 256), 256>>>(raw(name, "bias").d, pw.bias, pw.rows, 0, 0, nullptr);
+  I2IT_CUDA(cudaGetLastError());
+  prepared_[key] = pw;
+  return pw;
+}
+
 NormW Engine::norm(const std::string& name) {
   NormW n;
   const WT& g = raw(name, "weight");

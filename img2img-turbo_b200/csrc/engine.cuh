@@ -139,6 +139,7 @@ class Engine {
   PW prep(const std::string& cache_key, const std::vector<std::string>& names, bool geglu = false,
           float scale = 1.f, const float* bias_add = nullptr);
   PW prep_twin(const std::string& pre, const std::string& cur, float r);
+  PW prep_im2col3(const std::string& name);                        // 3x3 conv over 3 channels as a K=32 single-tap GEMM
   NormW norm(const std::string& name);
   const float* temb_bias(const std::string& resnet_prefix);          // time_emb_proj(silu(emb)) at t=999
   void free_prepared();

@@ -100,47 +100,57 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const uint32_t tS0 = tmem_base, tPV = tmem_base + 128;   // S buffers at columns [0,64) and [64,128)
 
   if (warp == 4) {
-    if (lane == 0) {
+    // producer: warp-uniform loop, one elected lane issues the TMA
+    if (elect_one()) {
       mbar_expect_tx(q_full, FA_Q_BYTES);
       tma_load_5d(sQ, &tmQ, q_full, 0, qt * FA_BM, h, b, 0);
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j % FA_STAGES;
-        mbar_wait(kv_empty(s), ((j / FA_STAGES) & 1) ^ 1, p.err, 11);
+    }
+    __syncwarp();
+    for (int j = 0; j < nkv; ++j) {
+      const int s = j % FA_STAGES;
+      mbar_wait(kv_empty(s), ((j / FA_STAGES) & 1) ^ 1, p.err, 11);
+      if (elect_one()) {
         mbar_expect_tx(kv_full(s), FA_KV_STAGE);
         tma_load_5d(sKV + s * FA_KV_STAGE, &tmK, kv_full(s), 0, j * FA_BN, h, b * p.kv_bmul, 0);
         tma_load_5d(sKV + s * FA_KV_STAGE + FA_BN * FA_D * 2, &tmVt, kv_full(s), j * FA_BN, 0, h, b * p.kv_bmul, 0);
       }
+      __syncwarp();
     }
   } else if (warp == 5) {
-    if (lane == 0) {
-      mbar_wait(q_full, 0, p.err, 12);
-      const uint64_t qdesc = umma_desc_sw128(sQ), pdesc = umma_desc_sw128(sP);
-      auto issue_qk = [&](int j) {
-        const int s = j % FA_STAGES;
-        mbar_wait(kv_full(s), (j / FA_STAGES) & 1, p.err, 13);
-        tc_fence_after();
+    // MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma / commit
+    mbar_wait(q_full, 0, p.err, 12);
+    const uint64_t qdesc = umma_desc_sw128(sQ), pdesc = umma_desc_sw128(sP);
+    auto issue_qk = [&](int j) {
+      const int s = j % FA_STAGES;
+      mbar_wait(kv_full(s), (j / FA_STAGES) & 1, p.err, 13);
+      tc_fence_after();
+      if (elect_one()) {
         const uint64_t kdesc = umma_desc_sw128(sKV + s * FA_KV_STAGE);
 #pragma unroll
         for (int k = 0; k < FA_D / 16; ++k)
           tc_mma_f16(tS0 + 64 * (j & 1), qdesc + 2 * k, kdesc + 2 * k, p.idesc, k > 0 ? 1u : 0u);
         tc_commit(s_full(j & 1));
-      };
-      issue_qk(0);
-      for (int j = 0; j < nkv; ++j) {
-        if (j + 1 < nkv) {
-          // S buffer (j+1)&1 was last read by softmax iteration j-1: QK_{j+1} overlaps the exponentials of iteration j
-          if (j >= 1) { mbar_wait(s_free((j + 1) & 1), ((j - 1) >> 1) & 1, p.err, 14); tc_fence_after(); }
-          issue_qk(j + 1);
-        }
-        mbar_wait(p_full, j & 1, p.err, 15);        // P_j is in smem (and PV_{j-1} has been consumed)
-        tc_fence_after();
-        const int s = j % FA_STAGES;
+      }
+      __syncwarp();
+    };
+    issue_qk(0);
+    for (int j = 0; j < nkv; ++j) {
+      if (j + 1 < nkv) {
+        // S buffer (j+1)&1 was last read by softmax iteration j-1: QK_{j+1} overlaps the exponentials of iteration j
+        if (j >= 1) { mbar_wait(s_free((j + 1) & 1), ((j - 1) >> 1) & 1, p.err, 14); tc_fence_after(); }
+        issue_qk(j + 1);
+      }
+      mbar_wait(p_full, j & 1, p.err, 15);        // P_j is in smem (and PV_{j-1} has been consumed)
+      tc_fence_after();
+      const int s = j % FA_STAGES;
+      if (elect_one()) {
         const uint64_t vdesc = umma_desc_sw128(sKV + s * FA_KV_STAGE + FA_BN * FA_D * 2);
 #pragma unroll
         for (int k = 0; k < FA_BN / 16; ++k) tc_mma_f16(tPV, pdesc + 2 * k, vdesc + 2 * k, p.idesc, k > 0 ? 1u : 0u);
         tc_commit(pv_full);
         tc_commit(kv_empty(s));                     // K_j and V_j are free once everything issued so far retires
       }
+      __syncwarp();
     }
   } else {
     // ---------------- softmax / output warps: thread = Q row ----------------

@@ -249,6 +249,34 @@ __global__ void pack_input_kernel(const T* __restrict__ x, T* __restrict__ y, in
   st16(y + i * 8, make_uint4(o[0], o[1], o[2], o[3]));
 }
 
+// NCHW [B,3,H,W] -> im2col rows [B,H,W,32]: k = (ky*3+kx)*3 + c for the 3x3 pad-1 neighbourhood (27 values, 5 zeros).
+// Turns encoder.conv_in (Cin=3: 16-byte TMA rows x 9 taps, TMA-request bound) into ONE K=32 GEMM tap with 64-byte rows.
+template <typename T>
+__global__ void pack_input_im2col_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // over B*H*W pixels
+  if (i >= total) return;
+  const long long HW = static_cast<long long>(H) * W;
+  const long long n = i / HW;
+  const int p = static_cast<int>(i % HW), py = p / W, px = p % W;
+  float v[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int yy = py + ky - 1, xx = px + kx - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[(ky * 3 + kx) * 3 + c] = Elem<T>::to_f(x[(n * 3 + c) * HW + static_cast<long long>(yy) * W + xx]);
+      }
+    }
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    st16(y + i * 32 + g * 8, make_uint4(Elem<T>::pack(v[8 * g], v[8 * g + 1]), Elem<T>::pack(v[8 * g + 2], v[8 * g + 3]),
+                                        Elem<T>::pack(v[8 * g + 4], v[8 * g + 5]), Elem<T>::pack(v[8 * g + 6], v[8 * g + 7])));
+}
+
 // DiagonalGaussianDistribution.sample() * scaling_factor (+ the stochastic blend of
 // /root/reference/src/pix2pix_turbo.py:210): moments NHWC (ld) -> latent NHWC8 (channels 4..7 zero).
 template <typename T>
@@ -359,6 +387,16 @@ __global__ void wprep_store_kernel(const float* __restrict__ acc, T* __restrict_
   orow += row_off;
   const float v = (ci < cin) ? acc[(static_cast<long long>(o) * cin + ci) * taps + t] * scale : 0.f;
   out[(static_cast<long long>(t) * rows_total + orow) * cin_pad + ci] = Elem<T>::from_f(v);
+}
+// acc [Cout][3][9] fp32 (3x3 conv over 3 channels) -> out[Cout][32] with k = tap*3 + c (matches pack_input_im2col_kernel)
+template <typename T>
+__global__ void wprep_store_im2col_kernel(const float* __restrict__ acc, T* __restrict__ out, int cout) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cout * 32) return;
+  const int o = i / 32, k = i % 32;
+  float v = 0.f;
+  if (k < 27) { const int t = k / 3, c = k % 3; v = acc[(o * 3 + c) * 9 + t]; }
+  out[i] = Elem<T>::from_f(v);
 }
 static __global__ void bias_store_kernel(const float* __restrict__ b, float* __restrict__ out, int cout, int row_off,
                                   int interleave_half, const float* __restrict__ add) {

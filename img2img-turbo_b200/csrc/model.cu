@@ -52,18 +52,22 @@ Act Engine::vae_attn(Plan& P, const std::string& p, const Act& x) {
 
 Act Engine::build_vae_encoder(Plan& P, const std::string& vp, int B, int H, int W, std::vector<Act>& skips) {
   const std::string e = vp + "encoder";
-  Act x8 = alloc_act(P, B, H, W, 8, 8, true);
+  // conv_in (3 -> C0, 3x3): the NCHW boundary tensor is packed straight into im2col rows [B,H,W,32] (27 taps*channels + 5
+  // zeros), so the conv is ONE K=32 GEMM tap with 64-byte TMA rows instead of nine taps of 16-byte rows
+  Act xcol = alloc_act(P, B, H, W, 32);
   {
-    const long long HW = static_cast<long long>(H) * W, total = HW * B;
-    uint16_t* yp = x8.p;
+    const long long total = static_cast<long long>(H) * W * B;
+    uint16_t* yp = xcol.p;
     Plan* plan = &P;
-    const int dt = dtype;
+    const int dt = dtype, hh = H, ww = W;
     add_op(P, [=](cudaStream_t st) {
-      DISPATCH_T(dt, (pack_input_kernel<T><<<ceil_div_i(total, 256), 256, 0, st>>>(
-                         reinterpret_cast<const T*>(plan->io.x), reinterpret_cast<T*>(yp), 3, HW, total)));
-    });
+      DISPATCH_T(dt, (pack_input_im2col_kernel<T><<<ceil_div_i(total, 128), 128, 0, st>>>(
+                         reinterpret_cast<const T*>(plan->io.x), reinterpret_cast<T*>(yp), hh, ww, total)));
+    }, "pack_im2col", 0, 2.0 * total * (3 + 32));
   }
-  Act s = conv(P, x8, prep(e + ".conv_in", {e + ".conv_in"}), ConvOpts());
+  ConvOpts oin; oin.ksize = 1;
+  Act s = conv(P, xcol, prep_im2col3(e + ".conv_in"), oin);
+  xcol = Act();
   for (int i = 0; i < 4; ++i) {
     skips.push_back(s);                                   // model.py:18-20: the INPUT of each down block
     mark(P, "skip" + std::to_string(i), s);

@@ -116,6 +116,16 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// one lane of a fully converged warp (warp-uniform control flow keeps descriptors/addresses in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -293,53 +303,55 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
   if (warp == 4) {
-    // ================================ TMA producer ================================
-    if (lane == 0) {
-      int stage = 0, phase = 0;
-      const uint32_t tx_bytes = TG_A_STAGE + static_cast<uint32_t>(p.BN) * (TG_BK * 2);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord c = decode_tile(p, tile);
-        const int a1 = c.t[0] * p.a_mul[0], a2 = c.t[1] * p.a_mul[1], a3 = c.t[2] * p.a_mul[2],
-                  a4 = c.t[3] * p.a_mul[3];
-        const int b2 = c.t[1] * p.b_mul[0], b3 = c.t[2] * p.b_mul[1], b4 = c.t[3] * p.b_mul[2];
-        const int n0 = c.nt * p.BN;
-        for (int t = 0; t < p.num_taps; ++t) {
-          const CUtensorMap* ta = p.tap_src[t] ? &tmA2 : &tmA;
-          const CUtensorMap* tb = p.tap_src[t] ? &tmB2 : &tmB;
-          const int nkc = p.tap_kc[t];
-          for (int kc = 0; kc < nkc; ++kc) {
-            mbar_wait(empty_bar(stage), phase ^ 1, p.err, 1);
+    // ================================ TMA producer (whole warp runs the loop, one elected lane issues) ==========
+    int stage = 0, phase = 0;
+    const uint32_t tx_bytes = TG_A_STAGE + static_cast<uint32_t>(p.BN) * (TG_BK * 2);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord c = decode_tile(p, tile);
+      const int a1 = c.t[0] * p.a_mul[0], a2 = c.t[1] * p.a_mul[1], a3 = c.t[2] * p.a_mul[2],
+                a4 = c.t[3] * p.a_mul[3];
+      const int b2 = c.t[1] * p.b_mul[0], b3 = c.t[2] * p.b_mul[1], b4 = c.t[3] * p.b_mul[2];
+      const int n0 = c.nt * p.BN;
+      for (int t = 0; t < p.num_taps; ++t) {
+        const CUtensorMap* ta = p.tap_src[t] ? &tmA2 : &tmA;
+        const CUtensorMap* tb = p.tap_src[t] ? &tmB2 : &tmB;
+        const int nkc = p.tap_kc[t];
+        for (int kc = 0; kc < nkc; ++kc) {
+          mbar_wait(empty_bar(stage), phase ^ 1, p.err, 1);
+          if (elect_one()) {
             mbar_expect_tx(full_bar(stage), tx_bytes);
             tma_load_5d(sA + stage * TG_A_STAGE, ta, full_bar(stage), kc * TG_BK + p.tap_a[t][0],
                         a1 + p.tap_a[t][1], a2 + p.tap_a[t][2], a3 + p.tap_a[t][3], a4 + p.tap_a[t][4]);
             tma_load_5d(sB + stage * TG_B_STAGE, tb, full_bar(stage), kc * TG_BK + p.tap_b[t][0], n0,
                         b2 + p.tap_b[t][1], b3 + p.tap_b[t][2], b4 + p.tap_b[t][3]);
-            if (++stage == TG_STAGES) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == TG_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 5) {
-    // ================================ MMA issuer ================================
-    if (lane == 0) {
-      int stage = 0, phase = 0, iter = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-        const int acc = iter & 1, aphase = (iter >> 1) & 1;
-        mbar_wait(tempty_bar(acc), aphase ^ 1, p.err, 2);
+    // ================================ MMA issuer (warp-uniform loop, elected lane issues) ================================
+    int stage = 0, phase = 0, iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      const int acc = iter & 1, aphase = (iter >> 1) & 1;
+      mbar_wait(tempty_bar(acc), aphase ^ 1, p.err, 2);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * TG_ACC_COLS;
+      for (int s = 0; s < steps; ++s) {
+        mbar_wait(full_bar(stage), phase, p.err, 3);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * TG_ACC_COLS;
-        for (int s = 0; s < steps; ++s) {
-          mbar_wait(full_bar(stage), phase, p.err, 3);
-          tc_fence_after();
+        if (elect_one()) {
           const uint64_t adesc = umma_desc_sw128(sA + stage * TG_A_STAGE);
           const uint64_t bdesc = umma_desc_sw128(sB + stage * TG_B_STAGE);
 #pragma unroll
           for (int k = 0; k < TG_BK / 16; ++k)
             tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (s > 0 || k > 0) ? 1u : 0u);
           tc_commit(empty_bar(stage));               // frees the smem slot when these MMAs retire
-          if (++stage == TG_STAGES) { stage = 0; phase ^= 1; }
+          if (s == steps - 1) tc_commit(tfull_bar(acc));   // accumulator complete -> epilogue
         }
-        tc_commit(tfull_bar(acc));                   // accumulator complete -> epilogue
+        __syncwarp();
+        if (++stage == TG_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else {
