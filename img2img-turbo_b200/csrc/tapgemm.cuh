@@ -381,37 +381,47 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
 
+      // Residual reads do not depend on the accumulator: round r+1's 32 columns are prefetched while round r is
+      // converted/stored, and round 0's before the accumulator wait, so global-load latency is off the per-tile path.
+      const int nrounds = (p.BN + 31) >> 5;
+      const bool res_on = p.res != nullptr && row_ok && p.rcol == 1 && p.act != TG_ACT_GEGLU;
+      auto prefetch = [&](int r, uint4 (&dst)[4]) -> bool {
+        if (!res_on || r >= nrounds) return false;
+        const int colg = n0 + 32 * r;
+        const int nch = min(2, (p.BN - 32 * r) >> 4);
+        const T* rgrp = reinterpret_cast<const T*>(p.res) + rbase + colg;
+        if (colg + 16 * nch > p.N || (reinterpret_cast<uintptr_t>(rgrp) & 15) != 0) return false;
+        dst[0] = ld_nc16(rgrp); dst[1] = ld_nc16(rgrp + 8);
+        if (nch == 2) { dst[2] = ld_nc16(rgrp + 16); dst[3] = ld_nc16(rgrp + 24); }
+        return true;
+      };
+      uint4 rqa[4], rqb[4];
+      bool fa = prefetch(0, rqa), fb = false;
+
       mbar_wait(tfull_bar(acc), aphase, p.err, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * TG_ACC_COLS;
 
-      // 64 columns per round: the residual prefetch and four TMEM loads are all in flight before anything is consumed
-      for (int c0 = 0; c0 < p.BN; c0 += 64) {
-        const int nch = min(4, (p.BN - c0) >> 4);
-        const int colg = n0 + c0;
-        // residual fast path: contiguous, 16-byte aligned, whole group inside N
-        uint4 rq[8];
-        const T* rgrp = p.res ? reinterpret_cast<const T*>(p.res) + rbase + colg : nullptr;
-        const bool rfast = p.res && row_ok && p.rcol == 1 && p.act != TG_ACT_GEGLU && (colg + 16 * nch <= p.N) &&
-                           ((reinterpret_cast<uintptr_t>(rgrp) & 15) == 0);
-        if (rfast) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (j < nch) { rq[2 * j] = ld_nc16(rgrp + 16 * j); rq[2 * j + 1] = ld_nc16(rgrp + 16 * j + 8); }
-        }
-        uint32_t raw[4][16];
+      auto do_round = [&](int r, const uint4 (&rq)[4], bool rfast) {
+        const int c0 = 32 * r;
+        const int nch = min(2, (p.BN - c0) >> 4);
+        uint32_t raw0[16], raw1[16];
         __syncwarp();                                // tcgen05.ld is .sync.aligned: reconverge after the guarded stores
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j < nch) tc_ld16(taddr + c0 + 16 * j, raw[j]);
+        tc_ld16(taddr + c0, raw0);
+        if (nch == 2) tc_ld16(taddr + c0 + 16, raw1);
         tc_wait_ld();
-        if (!row_ok) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j >= nch) continue;
-          const int col0 = colg + 16 * j;
-          if (col0 >= p.N) continue;
-          epilogue_chunk<T>(p, raw[j], col0, obase, rbase, rbias, sb + c0 + 16 * j, rfast, rq[2 * j], rq[2 * j + 1]);
+        if (!row_ok) return;
+        const int col0 = n0 + c0;
+        if (col0 < p.N) epilogue_chunk<T>(p, raw0, col0, obase, rbase, rbias, sb + c0, rfast, rq[0], rq[1]);
+        if (nch == 2 && col0 + 16 < p.N)
+          epilogue_chunk<T>(p, raw1, col0 + 16, obase, rbase, rbias, sb + c0 + 16, rfast, rq[2], rq[3]);
+      };
+      for (int r = 0; r < nrounds; r += 2) {
+        fb = prefetch(r + 1, rqb);
+        do_round(r, rqa, fa);
+        if (r + 1 < nrounds) {
+          fa = prefetch(r + 2, rqa);
+          do_round(r + 1, rqb, fb);
         }
       }
       tc_fence_before();
