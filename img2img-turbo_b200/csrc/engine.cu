@@ -337,6 +337,41 @@ PW Engine::prep_im2col3(const std::string& name) {
   return pw;
 }
 
+PW Engine::prep_subpixel(const std::string& name) {
+  const std::string key = name + "|subpixel";
+  auto it = prepared_.find(key);
+  if (it != prepared_.end()) return it->second;
+  const WT& w0 = raw(name, "weight");
+  I2IT_CHECK(w0.shape.size() == 4 && w0.shape[2] == 3 && w0.shape[3] == 3, "prep_subpixel: expects a 3x3 conv");
+  PW pw;
+  pw.rows = static_cast<int>(w0.shape[0]); pw.cin = static_cast<int>(w0.shape[1]); pw.cin_pad = round_up(pw.cin, 8); pw.taps = 16;
+  const long long total = 16ll * pw.rows * pw.cin_pad;
+  pw.w = static_cast<uint16_t*>(dmalloc(static_cast<size_t>(total) * 2));
+  pw.bias = static_cast<float*>(dmalloc(pw.rows * sizeof(float)));
+  long long numel = 0;
+  float* acc = fold_f32(name, &numel);
+  DISPATCH_T(dtype, (wprep_store_subpixel_kernel<T><<<ceil_div(total, 256), 256>>>(acc, reinterpret_cast<T*>(pw.w), pw.rows, pw.cin,
+                                                                                  pw.cin_pad, total)));
+  I2IT_CUDA(cudaMemset(pw.bias, 0, pw.rows * sizeof(float)));
+  bias_store_kernel<<<ceil_div(pw.rows, 256), 256>>>(raw(name, "bias").d, pw.bias, pw.rows, 0, 0, nullptr);
+  I2IT_CUDA(cudaGetLastError());
+  prepared_[key] = pw;
+  return pw;
+}
+
+// nearest-2x upsample + conv3x3 (+ optional folded 1x1 second source at output resolution) as four parity-phase launches
+Act Engine::conv_up2x(Plan& P, const Act& x, const PW& wsub, const Act* x2, const PW* w2) {
+  Act out = alloc_act(P, x.N, 2 * x.H, 2 * x.W, wsub.rows);
+  for (int ph = 0; ph < 4; ++ph) {
+    ConvOpts o;
+    o.subpixel_phase = ph;
+    o.out = &out;
+    o.x2 = x2; o.w2 = w2;
+    conv(P, x, wsub, o);
+  }
+  return out;
+}
+
 NormW Engine::norm(const std::string& name) {
   NormW n;
   const WT& g = raw(name, "weight");
@@ -452,8 +487,10 @@ static void fill_strides(TmapSpec& s) {
 }
 
 Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o) {
-  const int k = o.ksize, taps = k * k;
-  I2IT_CHECK(w.taps == taps, "conv: weight taps mismatch");
+  const bool sub = o.subpixel_phase >= 0;
+  const int k = o.ksize, taps = sub ? 4 : k * k;
+  I2IT_CHECK(sub ? (w.taps == 16 && k == 3 && o.stride == 1 && o.out && !o.res && !o.to_io_out_nchw) : (w.taps == taps),
+             "conv: weight taps mismatch");
   I2IT_CHECK(x.C == w.cin || x.C == w.cin_pad, "conv: input channels " + std::to_string(x.C) + " vs weight " +
                                                   std::to_string(w.cin));
   I2IT_CHECK(x.ld % 8 == 0, "conv: pixel stride must be a multiple of 8 elements");
@@ -490,14 +527,27 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o) {
     p.ext[0] = Wo; p.ext[1] = Ho; p.ext[2] = x.N; p.ext[3] = 1;
     p.a_mul[0] = tw; p.a_mul[1] = th; p.a_mul[2] = tn; p.a_mul[3] = 0;
     const int pad = k / 2;
-    for (int ky = 0; ky < k; ++ky)
-      for (int kx = 0; kx < k; ++kx) {
-        const int t = ky * k + kx;
-        p.tap_a[t][0] = 0; p.tap_a[t][1] = kx - pad; p.tap_a[t][2] = ky - pad; p.tap_a[t][3] = 0; p.tap_a[t][4] = 0;
-        p.tap_b[t][0] = 0; p.tap_b[t][1] = t; p.tap_b[t][2] = 0; p.tap_b[t][3] = 0;
-      }
-    p.ostride[0] = ldo; p.ostride[1] = static_cast<long long>(Wo) * ldo;
-    p.ostride[2] = static_cast<long long>(Ho) * Wo * ldo; p.ostride[3] = 0;
+    if (sub) {
+      // output parity (py,px): 2x2 taps at low-res offsets (ty-1+py, tx-1+px); output pixel (2y+py, 2x+px)
+      const int py = o.subpixel_phase >> 1, px = o.subpixel_phase & 1;
+      for (int ty = 0; ty < 2; ++ty)
+        for (int tx = 0; tx < 2; ++tx) {
+          const int t = ty * 2 + tx;
+          p.tap_a[t][0] = 0; p.tap_a[t][1] = tx - 1 + px; p.tap_a[t][2] = ty - 1 + py; p.tap_a[t][3] = 0; p.tap_a[t][4] = 0;
+          p.tap_b[t][0] = 0; p.tap_b[t][1] = o.subpixel_phase * 4 + t; p.tap_b[t][2] = 0; p.tap_b[t][3] = 0;
+        }
+      p.ostride[0] = 2 * ldo; p.ostride[1] = 2ll * (2 * Wo) * ldo;
+      p.ostride[2] = 4ll * Ho * Wo * ldo; p.ostride[3] = 0;
+    } else {
+      for (int ky = 0; ky < k; ++ky)
+        for (int kx = 0; kx < k; ++kx) {
+          const int t = ky * k + kx;
+          p.tap_a[t][0] = 0; p.tap_a[t][1] = kx - pad; p.tap_a[t][2] = ky - pad; p.tap_a[t][3] = 0; p.tap_a[t][4] = 0;
+          p.tap_b[t][0] = 0; p.tap_b[t][1] = t; p.tap_b[t][2] = 0; p.tap_b[t][3] = 0;
+        }
+      p.ostride[0] = ldo; p.ostride[1] = static_cast<long long>(Wo) * ldo;
+      p.ostride[2] = static_cast<long long>(Ho) * Wo * ldo; p.ostride[3] = 0;
+    }
     p.kchunks = ceil_div(x.C, 64);
   } else {
     I2IT_CHECK(o.stride == 2 && k == 3, "conv: only 3x3 stride-2 is on the path");
@@ -532,8 +582,8 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o) {
   fill_strides(sa);
 
   sb.base = w.w;
-  sb.dim[0] = w.cin_pad; sb.dim[1] = w.rows; sb.dim[2] = taps; sb.dim[3] = 1; sb.dim[4] = 1;
-  sb.stride[0] = w.cin_pad * 2ull; sb.stride[1] = 2ull * w.rows * w.cin_pad; sb.stride[2] = 2ull * taps * w.rows * w.cin_pad;
+  sb.dim[0] = w.cin_pad; sb.dim[1] = w.rows; sb.dim[2] = w.taps; sb.dim[3] = 1; sb.dim[4] = 1;
+  sb.stride[0] = w.cin_pad * 2ull; sb.stride[1] = 2ull * w.rows * w.cin_pad; sb.stride[2] = 2ull * w.taps * w.rows * w.cin_pad;
   sb.stride[3] = sb.stride[2];
   fill_strides(sb);
 
@@ -551,6 +601,9 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o) {
     const long long hw = static_cast<long long>(Ho) * Wo;
     p.ostride[0] = 1; p.ostride[1] = Wo; p.ostride[2] = hw * outc; p.ostride[3] = 0;
     p.ocol = hw;
+  } else if (sub) {
+    const int py = o.subpixel_phase >> 1, px = o.subpixel_phase & 1;
+    p.out = out.p + (static_cast<long long>(py) * (2 * Wo) + px) * ldo;
   } else {
     p.out = out.p;
   }
@@ -574,7 +627,8 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o) {
   if (o.x2) {
     // extra 1x1 "tap" over a second activation tensor with the same spatial geometry as the output
     I2IT_CHECK(o.w2 && o.stride == 1 && o.w2->taps == 1 && o.w2->rows == w.rows, "conv: bad second source");
-    I2IT_CHECK(o.x2->N == x.N && o.x2->H == Ho && o.x2->W == Wo && (o.x2->C == o.w2->cin || o.x2->C == o.w2->cin_pad),
+    const int sm = sub ? 2 : 1;     // sub-pixel: the second source lives at OUTPUT resolution, sampled at this parity
+    I2IT_CHECK(o.x2->N == x.N && o.x2->H == sm * Ho && o.x2->W == sm * Wo && (o.x2->C == o.w2->cin || o.x2->C == o.w2->cin_pad),
                "conv: second source shape mismatch");
     I2IT_CHECK(taps + 1 <= TG_MAX_TAPS, "conv: too many taps");
     TmapSpec sa2 = sa, sb2;
@@ -582,6 +636,11 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o) {
     sa2.dim[0] = o.x2->C;
     sa2.stride[0] = o.x2->ld * 2ull; sa2.stride[1] = 2ull * o.x2->W * o.x2->ld; sa2.stride[2] = 2ull * o.x2->H * o.x2->W * o.x2->ld;
     sa2.stride[3] = sa2.stride[2];
+    if (sub) {
+      const int py = o.subpixel_phase >> 1, px = o.subpixel_phase & 1;
+      sa2.base = o.x2->p + (static_cast<long long>(py) * o.x2->W + px) * o.x2->ld;
+      sa2.stride[0] = 2ull * o.x2->ld * 2; sa2.stride[1] = 2ull * 2 * o.x2->W * o.x2->ld;   // every other pixel / row
+    }
     fill_strides(sa2);
     sb2.base = o.w2->w;
     sb2.dim[0] = o.w2->cin_pad; sb2.dim[1] = o.w2->rows;
@@ -605,7 +664,7 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o) {
     const double m_valid = 1.0 * x.N * Ho * Wo, k_valid = 1.0 * taps * w.cin + k2;
     const double bytes = 2.0 * (1.0 * x.N * x.H * x.W * w.cin + m_valid * outc * (o.out_fp32 ? 2 : 1) + 1.0 * gemm_n * k_valid +
                                 (o.res ? m_valid * outc : 0) + m_valid * k2);
-    const char* kind = (k == 3) ? (o.stride == 2 ? "tapgemm:conv3x3s2" : "tapgemm:conv3x3") : "tapgemm:linear";
+    const char* kind = sub ? "tapgemm:conv_up2x" : (k == 3) ? (o.stride == 2 ? "tapgemm:conv3x3s2" : "tapgemm:conv3x3") : "tapgemm:linear";
     launch_gemm(P, ta, tb, p, grid, o.to_io_out_nchw, kind, k_valid, bytes, &ta2, &tb2);
   }
   return out;
@@ -626,9 +685,13 @@ Act Engine::group_norm(Plan& P, const Act& x, const NormW& nw, float eps, bool s
   I2IT_CHECK(x.C == nw.C && x.C % 32 == 0 && x.C % 8 == 0, "group_norm: bad channel count " + std::to_string(x.C));
   const int C = x.C, HW = x.H * x.W, cg = C / 32, vecs = C / 8;
   I2IT_CHECK(vecs <= 1024, "group_norm: too many channels");
-  const int rows = std::max(1, 256 / vecs), threads = vecs * rows;
-  const int chunks = std::max(1, std::min(256, ceil_div(HW, rows * 4)));
+  // tuning knobs (plan-build time): threads per CTA and CTAs per image
+  static const int env_thr = std::getenv("I2IT_GN_THREADS") ? atoi(std::getenv("I2IT_GN_THREADS")) : 128;   // measured best (r01 sweep)
+  static const int env_chunks = std::getenv("I2IT_GN_CHUNKS") ? atoi(std::getenv("I2IT_GN_CHUNKS")) : 512;
+  const int rows = std::max(1, std::min(1024, env_thr) / vecs), threads = vecs * rows;
+  const int chunks = std::max(1, std::min(env_chunks, ceil_div(HW, rows * 4)));
   const int pix = ceil_div(HW, chunks);
+  I2IT_CHECK(chunks <= 1024, "group_norm: too many chunks");
   auto partial = alloc_raw(P, static_cast<size_t>(x.N) * chunks * 64 * sizeof(float));
   auto stats = alloc_raw(P, static_cast<size_t>(x.N) * 64 * sizeof(float));
   Act y = alloc_act(P, x.N, x.H, x.W, C);

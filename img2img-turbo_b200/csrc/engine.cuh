@@ -93,6 +93,7 @@ struct ConvOpts {
   // second source folded into the same accumulator: out = conv(x) + conv1x1(x2)   (resnet conv_shortcut, decoder skip convs)
   const Act* x2 = nullptr;
   const PW* w2 = nullptr;
+  int subpixel_phase = -1;       // >=0: this launch is parity phase (py*2+px) of a fused nearest-2x-upsample + 3x3 conv
 };
 
 struct WT {                      // raw fp32 tensor of the state dict, on device
@@ -139,7 +140,9 @@ class Engine {
   PW prep(const std::string& cache_key, const std::vector<std::string>& names, bool geglu = false,
           float scale = 1.f, const float* bias_add = nullptr);
   PW prep_twin(const std::string& pre, const std::string& cur, float r);
-  PW prep_im2col3(const std::string& name);                        // 3x3 conv over 3 channels as a K=32 single-tap GEMM
+  PW prep_im2col3(const std::string& name);
+  PW prep_subpixel(const std::string& name);                       // 16 pre-summed 2x2 taps for upsample2x+conv3x3
+  Act conv_up2x(Plan& P, const Act& x, const PW& wsub, const Act* x2, const PW* w2);                        // 3x3 conv over 3 channels as a K=32 single-tap GEMM
   NormW norm(const std::string& name);
   const float* temb_bias(const std::string& resnet_prefix);          // time_emb_proj(silu(emb)) at t=999
   void free_prepared();

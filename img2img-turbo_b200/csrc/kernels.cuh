@@ -388,6 +388,30 @@ __global__ void wprep_store_kernel(const float* __restrict__ acc, T* __restrict_
   const float v = (ci < cin) ? acc[(static_cast<long long>(o) * cin + ci) * taps + t] * scale : 0.f;
   out[(static_cast<long long>(t) * rows_total + orow) * cin_pad + ci] = Elem<T>::from_f(v);
 }
+// nearest-2x upsample followed by a 3x3 pad-1 conv == four 2x2 convs on the LOW-RES tensor, one per output parity
+// (py,px), with pre-summed taps:  rows R(0,0)={0} R(0,1)={1,2} R(1,0)={0,1} R(1,1)={2}  (same for columns).
+// acc [Cout][Cin][9] fp32 -> out[phase*4 + ty*2+tx][Cout][cin_pad], phase = py*2+px.  Summed in fp32, rounded once.
+template <typename T>
+__global__ void wprep_store_subpixel_kernel(const float* __restrict__ acc, T* __restrict__ out, int cout, int cin,
+                                            int cin_pad, long long n /* 16*cout*cin_pad */) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int ci = static_cast<int>(i % cin_pad);
+  long long r = i / cin_pad;
+  const int o = static_cast<int>(r % cout);
+  const int t16 = static_cast<int>(r / cout);
+  const int phase = t16 >> 2, ty = (t16 >> 1) & 1, tx = t16 & 1, py = phase >> 1, px = phase & 1;
+  float v = 0.f;
+  if (ci < cin) {
+    const int ky0 = (py == 0) ? (ty == 0 ? 0 : 1) : (ty == 0 ? 0 : 2), ky1 = (py == 0) ? (ty == 0 ? 0 : 2) : (ty == 0 ? 1 : 2);
+    const int kx0 = (px == 0) ? (tx == 0 ? 0 : 1) : (tx == 0 ? 0 : 2), kx1 = (px == 0) ? (tx == 0 ? 0 : 2) : (tx == 0 ? 1 : 2);
+    const float* w = acc + (static_cast<long long>(o) * cin + ci) * 9;
+    for (int ky = ky0; ky <= ky1; ++ky)
+      for (int kx = kx0; kx <= kx1; ++kx) v += w[ky * 3 + kx];
+  }
+  out[i] = Elem<T>::from_f(v);
+}
+
 // acc [Cout][3][9] fp32 (3x3 conv over 3 channels) -> out[Cout][32] with k = tap*3 + c (matches pack_input_im2col_kernel)
 template <typename T>
 __global__ void wprep_store_im2col_kernel(const float* __restrict__ acc, T* __restrict__ out, int cout) {

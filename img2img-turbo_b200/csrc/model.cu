@@ -126,11 +126,11 @@ void Engine::build_vae_decoder(Plan& P, const std::string& vp, const Act& dec_in
   for (int i = 0; i < 4; ++i) {
     for (int j = 0; j < 3; ++j) s = vae_resnet(P, d + ".up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), s);
     if (i < 3) {
-      s = upsample2x(P, s);
+      // Upsample2D: nearest-2x + conv3x3, as four parity-phase 2x2 convs on the low-res tensor (2.25x fewer FLOPs, the
+      // upsampled tensor never exists); the next block's skip conv rides along as a second source at output resolution
       const std::string u = d + ".up_blocks." + std::to_string(i) + ".upsamplers.0.conv";
       PW wn = skip_w(i + 1);
-      ConvOpts ou; ou.x2 = &skips[2 - i]; ou.w2 = &wn;
-      s = conv(P, s, prep(u, {u}), ou);
+      s = conv_up2x(P, s, prep_subpixel(u), &skips[2 - i], &wn);
       skips[2 - i] = Act();
     }
     mark(P, "dec_up" + std::to_string(i), s);
