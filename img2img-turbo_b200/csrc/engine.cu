@@ -113,6 +113,9 @@ Engine::Engine(const i2it_config& c) : cfg(c), dtype(c.dtype) {
   I2IT_CUDA(cudaFuncSetAttribute(flash_attn_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
   I2IT_CUDA(cudaFuncSetAttribute(flash_attn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
   use_flash = std::getenv("I2IT_NO_FLASH") == nullptr;
+  use_pair = std::getenv("I2IT_NO_PAIR") == nullptr;
+  I2IT_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG2_SMEM));
+  I2IT_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG2_SMEM));
   int* h = nullptr;
   I2IT_CUDA(cudaHostAlloc(&h, sizeof(int), cudaHostAllocMapped));
   *h = 0;
@@ -460,24 +463,54 @@ int Engine::pick_bn(long long m_tiles, int N, bool) const {
   return best;
 }
 
-void Engine::launch_gemm(Plan& P, const CUtensorMap& ta, const CUtensorMap& tb, const TapGemmParams& p_in, int grid,
-                         bool out_from_io, const char* kind, double k_valid, double bytes, const CUtensorMap* ta2p,
-                         const CUtensorMap* tb2p) {
+void Engine::launch_gemm(Plan& P, const TmapSpec& sa, TmapSpec sb, const TapGemmParams& p_in, bool out_from_io,
+                         const char* kind, double k_valid, double bytes, const TmapSpec* sa2p, const TmapSpec* sb2p) {
   TapGemmParams p = p_in;
   for (int t = 0; t < p.num_taps; ++t)
     if (p.tap_kc[t] == 0) p.tap_kc[t] = p.kchunks;          // single-source callers only set kchunks
-  const CUtensorMap ta2 = ta2p ? *ta2p : ta, tb2 = tb2p ? *tb2p : tb;
+  const long long m_tiles = 1ll * p.tdim[0] * p.tdim[1] * p.tdim[2] * p.tdim[3];
+  const long long total_tiles = m_tiles * p.n_tiles;
+  // CTA-pair kernel: weights/B shared by every M tile (no per-tile B batch coordinates), enough tiles to fill the chip twice
+  const bool pair = use_pair && p.b_mul[0] == 0 && p.b_mul[1] == 0 && p.b_mul[2] == 0 && (p.BN % 32) == 0 &&
+                    total_tiles >= 2ll * num_sms && m_tiles >= 2;
+  TmapSpec sb2 = sb2p ? *sb2p : sb;
+  if (pair) { sb.box[1] = p.BN / 2; sb2.box[1] = p.BN / 2; p.idesc = make_idesc2(dtype, p.BN); }
+  const CUtensorMap ta = encode_tmap(sa, dtype), tb = encode_tmap(sb, dtype);
+  const CUtensorMap ta2 = sa2p ? encode_tmap(*sa2p, dtype) : ta, tb2 = sb2p ? encode_tmap(sb2, dtype) : tb;
   const int dt = dtype;
   Plan* plan = &P;
   const double m_valid = 1.0 * p.ext[0] * p.ext[1] * p.ext[2] * p.ext[3];
+  int grid;
+  if (pair) {
+    const long long pairs = ((m_tiles + 1) / 2) * p.n_tiles;
+    grid = 2 * static_cast<int>(std::min<long long>(pairs, num_sms / 2));
+  } else {
+    grid = static_cast<int>(std::min<long long>(total_tiles, num_sms));
+  }
   char shp[160];
-  snprintf(shp, sizeof shp, "M=%.0f N=%d K=%.0f taps=%d BN=%d tiles=%d grid=%d", m_valid, p.N, k_valid, p.num_taps, p.BN,
-           p.n_tiles * p.tdim[0] * p.tdim[1] * p.tdim[2] * p.tdim[3], grid);
-  add_op(P, [ta, tb, ta2, tb2, p, grid, dt, out_from_io, plan](cudaStream_t st) {
-    TapGemmParams q = p;
-    if (out_from_io) q.out = plan->io.out;
-    DISPATCH_T(dt, (tapgemm_kernel<T><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, ta2, tb2, q)));
-  }, kind, 2.0 * m_valid * p.N * k_valid, bytes, shp);
+  snprintf(shp, sizeof shp, "M=%.0f N=%d K=%.0f taps=%d BN=%d tiles=%lld grid=%d%s", m_valid, p.N, k_valid, p.num_taps, p.BN,
+           total_tiles, grid, pair ? " pair" : "");
+  if (pair) {
+    add_op(P, [ta, tb, ta2, tb2, p, grid, dt, out_from_io, plan](cudaStream_t st) {
+      TapGemmParams q = p;
+      if (out_from_io) q.out = plan->io.out;
+      cudaLaunchConfig_t cfg;
+      std::memset(&cfg, 0, sizeof cfg);
+      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TG_THREADS); cfg.dynamicSmemBytes = TG2_SMEM; cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      if (dt == DT_BF16) cudaLaunchKernelEx(&cfg, tapgemm2_kernel<__nv_bfloat16>, ta, tb, ta2, tb2, q);
+      else cudaLaunchKernelEx(&cfg, tapgemm2_kernel<__half>, ta, tb, ta2, tb2, q);
+    }, kind, 2.0 * m_valid * p.N * k_valid, bytes, shp);
+  } else {
+    add_op(P, [ta, tb, ta2, tb2, p, grid, dt, out_from_io, plan](cudaStream_t st) {
+      TapGemmParams q = p;
+      if (out_from_io) q.out = plan->io.out;
+      DISPATCH_T(dt, (tapgemm_kernel<T><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, ta2, tb2, q)));
+    }, kind, 2.0 * m_valid * p.N * k_valid, bytes, shp);
+  }
 }
 
 static void fill_strides(TmapSpec& s) {
@@ -621,8 +654,7 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o) {
   p.act = o.act;
   p.err = d_err;
 
-  const CUtensorMap ta = encode_tmap(sa, dtype), tb = encode_tmap(sb, dtype);
-  CUtensorMap ta2 = ta, tb2 = tb;
+  TmapSpec sa2, sb2;
   double k2 = 0;
   if (o.x2) {
     // extra 1x1 "tap" over a second activation tensor with the same spatial geometry as the output
@@ -631,7 +663,7 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o) {
     I2IT_CHECK(o.x2->N == x.N && o.x2->H == sm * Ho && o.x2->W == sm * Wo && (o.x2->C == o.w2->cin || o.x2->C == o.w2->cin_pad),
                "conv: second source shape mismatch");
     I2IT_CHECK(taps + 1 <= TG_MAX_TAPS, "conv: too many taps");
-    TmapSpec sa2 = sa, sb2;
+    sa2 = sa;
     sa2.base = o.x2->p;
     sa2.dim[0] = o.x2->C;
     sa2.stride[0] = o.x2->ld * 2ull; sa2.stride[1] = 2ull * o.x2->W * o.x2->ld; sa2.stride[2] = 2ull * o.x2->H * o.x2->W * o.x2->ld;
@@ -648,8 +680,6 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o) {
     sb2.stride[3] = sb2.stride[1];
     sb2.box[0] = 64; sb2.box[1] = p.BN;
     fill_strides(sb2);
-    ta2 = encode_tmap(sa2, dtype);
-    tb2 = encode_tmap(sb2, dtype);
     for (int t = 0; t < taps; ++t) { p.tap_src[t] = 0; p.tap_kc[t] = p.kchunks; }
     const int t2 = taps;
     for (int d = 0; d < 5; ++d) p.tap_a[t2][d] = 0;
@@ -659,13 +689,12 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o) {
     p.num_taps = taps + 1;
     k2 = o.w2->cin;
   }
-  const int grid = static_cast<int>(std::min<long long>(m_tiles * p.n_tiles, num_sms));
   {
     const double m_valid = 1.0 * x.N * Ho * Wo, k_valid = 1.0 * taps * w.cin + k2;
     const double bytes = 2.0 * (1.0 * x.N * x.H * x.W * w.cin + m_valid * outc * (o.out_fp32 ? 2 : 1) + 1.0 * gemm_n * k_valid +
                                 (o.res ? m_valid * outc : 0) + m_valid * k2);
     const char* kind = sub ? "tapgemm:conv_up2x" : (k == 3) ? (o.stride == 2 ? "tapgemm:conv3x3s2" : "tapgemm:conv3x3") : "tapgemm:linear";
-    launch_gemm(P, ta, tb, p, grid, o.to_io_out_nchw, kind, k_valid, bytes, &ta2, &tb2);
+    launch_gemm(P, sa, sb, p, o.to_io_out_nchw, kind, k_valid, bytes, o.x2 ? &sa2 : nullptr, o.x2 ? &sb2 : nullptr);
   }
   return out;
 }
@@ -797,8 +826,7 @@ Act Engine::vt_proj(Plan& P, const Act& x, int B, int ntok, const PW& wv) {
   p.bias_mode = wv.bias ? TG_BIAS_ROW : TG_BIAS_NONE;
   p.alpha = 1.f;
   p.err = d_err;
-  const CUtensorMap ta = encode_tmap(sa, dtype), tb = encode_tmap(sb, dtype);
-  launch_gemm(P, ta, tb, p, static_cast<int>(std::min<long long>(m_tiles * p.n_tiles, num_sms)), false, "tapgemm:vt",
+  launch_gemm(P, sa, sb, p, false, "tapgemm:vt",
               wv.cin, 2.0 * (1.0 * C * wv.cin + 1.0 * B * ntok * wv.cin + 1.0 * B * C * ntok));
   return vt;
 }
@@ -850,8 +878,7 @@ Act Engine::attention(Plan& P, const Act& q, const Act& k, const Act& vt, int B,
     p.ocol = 1;
     p.alpha = 1.0f / sqrtf(static_cast<float>(d));
     p.err = d_err;
-    const CUtensorMap ta = encode_tmap(sa, dtype), tb = encode_tmap(sb, dtype);
-    launch_gemm(P, ta, tb, p, static_cast<int>(std::min<long long>(m_tiles * p.n_tiles, num_sms)), false, "tapgemm:attn_qk", d,
+    launch_gemm(P, sa, sb, p, false, "tapgemm:attn_qk", d,
                 2.0 * B * heads * (1.0 * Nq * d + 1.0 * Nk * d) + 4.0 * rows * Nk);
   }
   {  // P = softmax(S)
@@ -900,8 +927,7 @@ Act Engine::attention(Plan& P, const Act& q, const Act& k, const Act& vt, int B,
     p.ocol = 1;
     p.alpha = 1.f;
     p.err = d_err;
-    const CUtensorMap ta = encode_tmap(sa, dtype), tb = encode_tmap(sb, dtype);
-    launch_gemm(P, ta, tb, p, static_cast<int>(std::min<long long>(m_tiles * p.n_tiles, num_sms)), false, "tapgemm:attn_pv", Nk,
+    launch_gemm(P, sa, sb, p, false, "tapgemm:attn_pv", Nk,
                 2.0 * (1.0 * rows * Nk + 1.0 * B * heads * Nk * d + 1.0 * rows * d));
   }
   return out;

@@ -13,6 +13,7 @@
 #include "kernels.cuh"
 #include "tapgemm.cuh"
 #include "flash.cuh"
+#include "tapgemm2.cuh"
 
 namespace i2it {
 
@@ -163,9 +164,10 @@ class Engine {
     OpMeta m; m.kind = kind; m.flops = flops; m.bytes = bytes; m.shape = shape;
     P.meta.push_back(m);
   }
-  void launch_gemm(Plan& P, const CUtensorMap& ta, const CUtensorMap& tb, const TapGemmParams& p, int grid,
-                   bool out_from_io, const char* kind, double k_valid, double bytes, const CUtensorMap* ta2 = nullptr,
-                   const CUtensorMap* tb2 = nullptr);
+  // encodes the tensor maps and appends the launch; picks the CTA-pair kernel (tapgemm2) for big conv/linear layers
+  void launch_gemm(Plan& P, const TmapSpec& sa, TmapSpec sb, const TapGemmParams& p, bool out_from_io, const char* kind,
+                   double k_valid, double bytes, const TmapSpec* sa2 = nullptr, const TmapSpec* sb2 = nullptr);
+  bool use_pair = true;
   std::string profile_json(int reps, cudaStream_t st);
   int pick_bn(long long m_tiles, int N, bool even32) const;
 

@@ -261,6 +261,73 @@ __device__ __forceinline__ void epilogue_chunk(const TapGemmParams& p, const uin
   }
 }
 
+// The whole epilogue of one output tile for one thread (= one accumulator row): bias slice staged in smem, residual
+// prefetched a round ahead, accumulator pulled from TMEM 32 columns at a time, single rounding, 64-byte stores.
+// Shared by the 1-CTA and the 2-CTA kernels.  Caller signals tmem_empty afterwards.
+template <typename T>
+__device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const TileCoord& c, int row, int warp, int j1, int j2,
+                                              int j3, int j4, int acc, int aphase, uint32_t tmem_base, float* s_bias,
+                                              uint32_t tfull_bar_addr) {
+  const int g1 = c.t[0] * p.box[0] + j1, g2 = c.t[1] * p.box[1] + j2, g3 = c.t[2] * p.box[2] + j3,
+            g4 = c.t[3] * p.box[3] + j4;
+  const bool row_ok = (g1 < p.ext[0]) && (g2 < p.ext[1]) && (g3 < p.ext[2]) && (g4 < p.ext[3]);
+  const long long obase = g1 * p.ostride[0] + g2 * p.ostride[1] + g3 * p.ostride[2] + g4 * p.ostride[3];
+  const long long rbase = g1 * p.rstride[0] + g2 * p.rstride[1] + g3 * p.rstride[2] + g4 * p.rstride[3];
+  const float rbias = (p.bias_mode == TG_BIAS_ROW && row_ok) ? p.bias[g1] : 0.0f;
+  const int n0 = c.nt * p.BN;
+
+  // stage this tile's bias slice in smem once (a per-chunk global load here stalled the whole epilogue: r01 ncu)
+  float* sb = s_bias + acc * 256;
+  if (p.bias_mode == TG_BIAS_COL) {
+    for (int cc = row; cc < p.BN; cc += 128) sb[cc] = (n0 + cc < p.N) ? p.bias[n0 + cc] : 0.f;
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+
+  // Residual reads do not depend on the accumulator: round r+1's 32 columns are prefetched while round r is
+  // converted/stored, and round 0's before the accumulator wait, so global-load latency is off the per-tile path.
+  const int nrounds = (p.BN + 31) >> 5;
+  const bool res_on = p.res != nullptr && row_ok && p.rcol == 1 && p.act != TG_ACT_GEGLU;
+  auto prefetch = [&](int r, uint4 (&dst)[4]) -> bool {
+    if (!res_on || r >= nrounds) return false;
+    const int colg = n0 + 32 * r;
+    const int nch = min(2, (p.BN - 32 * r) >> 4);
+    const T* rgrp = reinterpret_cast<const T*>(p.res) + rbase + colg;
+    if (colg + 16 * nch > p.N || (reinterpret_cast<uintptr_t>(rgrp) & 15) != 0) return false;
+    dst[0] = ld_nc16(rgrp); dst[1] = ld_nc16(rgrp + 8);
+    if (nch == 2) { dst[2] = ld_nc16(rgrp + 16); dst[3] = ld_nc16(rgrp + 24); }
+    return true;
+  };
+  uint4 rqa[4], rqb[4];
+  bool fa = prefetch(0, rqa), fb = false;
+
+  mbar_wait(tfull_bar_addr, aphase, p.err, 4);
+  tc_fence_after();
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * TG_ACC_COLS;
+
+  auto do_round = [&](int r, const uint4 (&rq)[4], bool rfast) {
+    const int c0 = 32 * r;
+    const int nch = min(2, (p.BN - c0) >> 4);
+    uint32_t raw0[16], raw1[16];
+    __syncwarp();                                // tcgen05.ld is .sync.aligned: reconverge after the guarded stores
+    tc_ld16(taddr + c0, raw0);
+    if (nch == 2) tc_ld16(taddr + c0 + 16, raw1);
+    tc_wait_ld();
+    if (!row_ok) return;
+    const int col0 = n0 + c0;
+    if (col0 < p.N) epilogue_chunk<T>(p, raw0, col0, obase, rbase, rbias, sb + c0, rfast, rq[0], rq[1]);
+    if (nch == 2 && col0 + 16 < p.N)
+      epilogue_chunk<T>(p, raw1, col0 + 16, obase, rbase, rbias, sb + c0 + 16, rfast, rq[2], rq[3]);
+  };
+  for (int r = 0; r < nrounds; r += 2) {
+    fb = prefetch(r + 1, rqb);
+    do_round(r, rqa, fa);
+    if (r + 1 < nrounds) {
+      fa = prefetch(r + 2, rqa);
+      do_round(r + 1, rqb, fb);
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -366,64 +433,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       const int acc = iter & 1, aphase = (iter >> 1) & 1;
       const TileCoord c = decode_tile(p, tile);
-      const int g1 = c.t[0] * p.box[0] + j1, g2 = c.t[1] * p.box[1] + j2, g3 = c.t[2] * p.box[2] + j3,
-                g4 = c.t[3] * p.box[3] + j4;
-      const bool row_ok = (g1 < p.ext[0]) && (g2 < p.ext[1]) && (g3 < p.ext[2]) && (g4 < p.ext[3]);
-      const long long obase = g1 * p.ostride[0] + g2 * p.ostride[1] + g3 * p.ostride[2] + g4 * p.ostride[3];
-      const long long rbase = g1 * p.rstride[0] + g2 * p.rstride[1] + g3 * p.rstride[2] + g4 * p.rstride[3];
-      const float rbias = (p.bias_mode == TG_BIAS_ROW && row_ok) ? p.bias[g1] : 0.0f;
-      const int n0 = c.nt * p.BN;
-
-      // stage this tile's bias slice in smem once (a per-chunk global load here stalled the whole epilogue: r01 ncu)
-      float* sb = s_bias + acc * 256;
-      if (p.bias_mode == TG_BIAS_COL) {
-        for (int cc = row; cc < p.BN; cc += 128) sb[cc] = (n0 + cc < p.N) ? p.bias[n0 + cc] : 0.f;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
-
-      // Residual reads do not depend on the accumulator: round r+1's 32 columns are prefetched while round r is
-      // converted/stored, and round 0's before the accumulator wait, so global-load latency is off the per-tile path.
-      const int nrounds = (p.BN + 31) >> 5;
-      const bool res_on = p.res != nullptr && row_ok && p.rcol == 1 && p.act != TG_ACT_GEGLU;
-      auto prefetch = [&](int r, uint4 (&dst)[4]) -> bool {
-        if (!res_on || r >= nrounds) return false;
-        const int colg = n0 + 32 * r;
-        const int nch = min(2, (p.BN - 32 * r) >> 4);
-        const T* rgrp = reinterpret_cast<const T*>(p.res) + rbase + colg;
-        if (colg + 16 * nch > p.N || (reinterpret_cast<uintptr_t>(rgrp) & 15) != 0) return false;
-        dst[0] = ld_nc16(rgrp); dst[1] = ld_nc16(rgrp + 8);
-        if (nch == 2) { dst[2] = ld_nc16(rgrp + 16); dst[3] = ld_nc16(rgrp + 24); }
-        return true;
-      };
-      uint4 rqa[4], rqb[4];
-      bool fa = prefetch(0, rqa), fb = false;
-
-      mbar_wait(tfull_bar(acc), aphase, p.err, 4);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * TG_ACC_COLS;
-
-      auto do_round = [&](int r, const uint4 (&rq)[4], bool rfast) {
-        const int c0 = 32 * r;
-        const int nch = min(2, (p.BN - c0) >> 4);
-        uint32_t raw0[16], raw1[16];
-        __syncwarp();                                // tcgen05.ld is .sync.aligned: reconverge after the guarded stores
-        tc_ld16(taddr + c0, raw0);
-        if (nch == 2) tc_ld16(taddr + c0 + 16, raw1);
-        tc_wait_ld();
-        if (!row_ok) return;
-        const int col0 = n0 + c0;
-        if (col0 < p.N) epilogue_chunk<T>(p, raw0, col0, obase, rbase, rbias, sb + c0, rfast, rq[0], rq[1]);
-        if (nch == 2 && col0 + 16 < p.N)
-          epilogue_chunk<T>(p, raw1, col0 + 16, obase, rbase, rbias, sb + c0 + 16, rfast, rq[2], rq[3]);
-      };
-      for (int r = 0; r < nrounds; r += 2) {
-        fb = prefetch(r + 1, rqb);
-        do_round(r, rqa, fa);
-        if (r + 1 < nrounds) {
-          fa = prefetch(r + 2, rqa);
-          do_round(r + 1, rqb, fb);
-        }
-      }
+      epilogue_tile<T>(p, c, row, warp, j1, j2, j3, j4, acc, aphase, tmem_base, s_bias, tfull_bar(acc));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));

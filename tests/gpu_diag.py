@@ -161,6 +161,13 @@ CASES = {
     "attn_cross": lambda: case_attn(hf, 2, 256, 77, 5, 64, kvb=1),
     "attn_4096": lambda: case_attn(bf, 1, 4096, 4096, 2, 64),
     "attn_vae": lambda: case_attn(bf, 1, 1024, 1024, 1, 512),
+    # big enough (>= 2 x 148 tiles) to take the CTA-pair (cta_group::2) kernel
+    "pair_conv": lambda: case_conv(bf, 4, 128, 128, 128, 128, res=True),
+    "pair_conv256": lambda: case_conv(hf, 2, 128, 128, 256, 256),
+    "pair_lin": lambda: case_linear(bf, 65536, 320, 320, res=True),
+    "pair_lin_odd": lambda: case_linear(hf, 128 * 301 + 17, 256, 512),
+    "pair_geglu": lambda: case_conv(bf, 1, 1, 32768, 320, 2560, k=1, act=i2it.ACT_GEGLU),
+    "pair_s2": lambda: case_conv(bf, 4, 256, 256, 128, 128, stride=2, asym=True),
     "attn_small": lambda: case_attn(hf, 3, 64, 64, 20, 64),
     "attn_ragged": lambda: case_attn(bf, 2, 200, 150, 2, 64),
     "attn_1024": lambda: case_attn(hf, 2, 1024, 1024, 10, 64),
