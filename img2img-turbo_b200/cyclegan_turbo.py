@@ -133,7 +133,7 @@ class CycleGAN_Turbo(TurboBase):
         if text.shape[0] not in (1, B):
             raise ValueError("caption embedding batch must be 1 or match the image batch")
         eng = self._finalize(1.0, 1.0, 1.0, -1.0)
-        out = eng.forward(xd, text, eps, direction=i2it.A2B if direction == "a2b" else i2it.B2A)
+        out = self._staged_forward(eng, xd, text, eps, direction=i2it.A2B if direction == "a2b" else i2it.B2A)
         return out if in_dtype == dt else out.to(in_dtype)
 
     @staticmethod

@@ -146,7 +146,7 @@ class Pix2Pix_Turbo(TurboBase):
             if self._twin:
                 raise TypeError("deterministic forward on a TwinConv model: conv_in.r is None (as in the reference)")
             eng = self._finalize(self._lora_w_unet, self._lora_w_vae, float(self.vae.decoder.gamma), -1.0)
-            out = eng.forward(x, caption_enc, eps)
+            out = self._staged_forward(eng, x, caption_enc, eps)
         else:
             if noise_map is None:
                 raise ValueError("noise_map is required when deterministic=False")
@@ -156,7 +156,7 @@ class Pix2Pix_Turbo(TurboBase):
             self.vae.decoder.gamma = r
             eng = self._finalize(r, r, r, r if self._twin else -1.0)
             nm = self._prep(noise_map.expand(B, -1, -1, -1) if noise_map.shape[0] != B else noise_map, dt)
-            out = eng.forward(x, caption_enc, eps, noise_map=nm, r=float(r))
+            out = self._staged_forward(eng, x, caption_enc, eps, noise=nm, r=float(r))
             if self._twin:
                 self.unet.conv_in.r = None
         return out if in_dtype == dt else out.to(in_dtype)
