@@ -114,6 +114,8 @@ Engine::Engine(const i2it_config& c) : cfg(c), dtype(c.dtype) {
   I2IT_CUDA(cudaFuncSetAttribute(flash_attn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
   use_flash = std::getenv("I2IT_NO_FLASH") == nullptr;
   use_pair = std::getenv("I2IT_NO_PAIR") == nullptr;
+  use_idres = std::getenv("I2IT_NO_IDRES") == nullptr;
+  use_halo = std::getenv("I2IT_HALO") != nullptr;     // experimental (r01: descriptor semantics of shifted swizzled views unresolved -> wrong results); off by default
   I2IT_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG2_SMEM));
   I2IT_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG2_SMEM));
   int* h = nullptr;
@@ -340,6 +342,19 @@ PW Engine::prep_im2col3(const std::string& name) {
   return pw;
 }
 
+PW Engine::prep_identity(int n) {
+  const std::string key = "identity|" + std::to_string(n);
+  auto it = prepared_.find(key);
+  if (it != prepared_.end()) return it->second;
+  PW pw;
+  pw.rows = n; pw.cin = n; pw.cin_pad = n; pw.taps = 1;
+  pw.w = static_cast<uint16_t*>(dmalloc(static_cast<size_t>(n) * n * 2));
+  DISPATCH_T(dtype, (identity_store_kernel<T><<<ceil_div(1ll * n * n, 256), 256>>>(reinterpret_cast<T*>(pw.w), n)));
+  I2IT_CUDA(cudaGetLastError());
+  prepared_[key] = pw;
+  return pw;
+}
+
 PW Engine::prep_subpixel(const std::string& name) {
   const std::string key = name + "|subpixel";
   auto it = prepared_.find(key);
@@ -464,10 +479,12 @@ int Engine::pick_bn(long long m_tiles, int N, bool) const {
 }
 
 void Engine::launch_gemm(Plan& P, const TmapSpec& sa, TmapSpec sb, const TapGemmParams& p_in, bool out_from_io,
-                         const char* kind, double k_valid, double bytes, const TmapSpec* sa2p, const TmapSpec* sb2p) {
+                         const char* kind, double k_valid, double bytes, const TmapSpec* sa2p, const TmapSpec* sb2p,
+                         const TmapSpec* shalo) {
   TapGemmParams p = p_in;
   for (int t = 0; t < p.num_taps; ++t)
     if (p.tap_kc[t] == 0) p.tap_kc[t] = p.kchunks;          // single-source callers only set kchunks
+  if (p.nprim == 0) p.nprim = p.num_taps;
   const long long m_tiles = 1ll * p.tdim[0] * p.tdim[1] * p.tdim[2] * p.tdim[3];
   const long long total_tiles = m_tiles * p.n_tiles;
   // CTA-pair kernel: weights/B shared by every M tile (no per-tile B batch coordinates), enough tiles to fill the chip twice
@@ -475,7 +492,9 @@ void Engine::launch_gemm(Plan& P, const TmapSpec& sa, TmapSpec sb, const TapGemm
                     total_tiles >= 2ll * num_sms && m_tiles >= 2;
   TmapSpec sb2 = sb2p ? *sb2p : sb;
   if (pair) { sb.box[1] = p.BN / 2; sb2.box[1] = p.BN / 2; p.idesc = make_idesc2(dtype, p.BN); }
+  p.halo = (pair && shalo != nullptr && use_halo) ? 1 : 0;
   const CUtensorMap ta = encode_tmap(sa, dtype), tb = encode_tmap(sb, dtype);
+  const CUtensorMap th = p.halo ? encode_tmap(*shalo, dtype) : ta;
   const CUtensorMap ta2 = sa2p ? encode_tmap(*sa2p, dtype) : ta, tb2 = sb2p ? encode_tmap(sb2, dtype) : tb;
   const int dt = dtype;
   Plan* plan = &P;
@@ -489,9 +508,9 @@ void Engine::launch_gemm(Plan& P, const TmapSpec& sa, TmapSpec sb, const TapGemm
   }
   char shp[160];
   snprintf(shp, sizeof shp, "M=%.0f N=%d K=%.0f taps=%d BN=%d tiles=%lld grid=%d%s", m_valid, p.N, k_valid, p.num_taps, p.BN,
-           total_tiles, grid, pair ? " pair" : "");
+           total_tiles, grid, pair ? (p.halo ? " pair halo" : " pair") : "");
   if (pair) {
-    add_op(P, [ta, tb, ta2, tb2, p, grid, dt, out_from_io, plan](cudaStream_t st) {
+    add_op(P, [ta, tb, ta2, tb2, th, p, grid, dt, out_from_io, plan](cudaStream_t st) {
       TapGemmParams q = p;
       if (out_from_io) q.out = plan->io.out;
       cudaLaunchConfig_t cfg;
@@ -501,8 +520,8 @@ void Engine::launch_gemm(Plan& P, const TmapSpec& sa, TmapSpec sb, const TapGemm
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
-      if (dt == DT_BF16) cudaLaunchKernelEx(&cfg, tapgemm2_kernel<__nv_bfloat16>, ta, tb, ta2, tb2, q);
-      else cudaLaunchKernelEx(&cfg, tapgemm2_kernel<__half>, ta, tb, ta2, tb2, q);
+      if (dt == DT_BF16) cudaLaunchKernelEx(&cfg, tapgemm2_kernel<__nv_bfloat16>, ta, tb, ta2, tb2, th, q);
+      else cudaLaunchKernelEx(&cfg, tapgemm2_kernel<__half>, ta, tb, ta2, tb2, th, q);
     }, kind, 2.0 * m_valid * p.N * k_valid, bytes, shp);
   } else {
     add_op(P, [ta, tb, ta2, tb2, p, grid, dt, out_from_io, plan](cudaStream_t st) {
@@ -519,7 +538,18 @@ static void fill_strides(TmapSpec& s) {
     if (s.stride[i] == 0 || (s.stride[i] % 16) != 0) s.stride[i] = 16;
 }
 
-Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o) {
+Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o_in) {
+  // A 3x3 conv's identity residual becomes one more K-slab (second source x identity weights): exact (bf16 * 1.0 accumulated
+  // in fp32) and it rides the TMA pipeline instead of latency-bound epilogue loads (+1/9 MMA work; r01: 0.85 -> see profiles)
+  if (use_idres && o_in.res && !o_in.x2 && o_in.ksize == 3 && o_in.stride == 1 && o_in.subpixel_phase < 0 && !o_in.out_fp32 &&
+      o_in.act != TG_ACT_GEGLU && o_in.res->C == w.rows && w.rows % 8 == 0 && w.rows <= 256 /* wider layers are MMA-bound */ && o_in.res->N == x.N && o_in.res->H == x.H &&
+      o_in.res->W == x.W) {
+    ConvOpts o2 = o_in;
+    const PW ident = prep_identity(w.rows);
+    o2.x2 = o_in.res; o2.w2 = &ident; o2.res = nullptr; o2.x2_identity = true;
+    return conv(P, x, w, o2);
+  }
+  const ConvOpts& o = o_in;
   const bool sub = o.subpixel_phase >= 0;
   const int k = o.ksize, taps = sub ? 4 : k * k;
   I2IT_CHECK(sub ? (w.taps == 16 && k == 3 && o.stride == 1 && o.out && !o.res && !o.to_io_out_nchw) : (w.taps == taps),
@@ -546,10 +576,14 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o) {
   std::memset(&p, 0, sizeof p);
   int tw, th, tn;
   const long long ldo = o.to_io_out_nchw ? 0 : out.ld;
+  // halo mode (CTA-pair kernel): 8 x 16 output tiles whose nine taps share one halo tile per k-chunk
+  const bool want_halo = use_halo && use_pair && o.stride == 1 && k == 3 && !sub && !o.x2 && !o.to_io_out_nchw && x.H >= 16 &&
+                         x.W >= 8 && x.C % 64 == 0;
   if (o.stride == 1) {
     tw = (x.H == 1) ? std::min(128, pow2ceil(x.W)) : std::min(o.to_io_out_nchw ? 32 : 16, pow2ceil(x.W));
     th = std::min(128 / tw, pow2ceil(x.H));
     tn = 128 / (tw * th);
+    if (want_halo) { tw = 8; th = 16; tn = 1; }
     sa.base = x.p;
     sa.dim[0] = x.C; sa.dim[1] = x.W; sa.dim[2] = x.H; sa.dim[3] = x.N; sa.dim[4] = 1;
     sa.stride[0] = x.ld * 2ull; sa.stride[1] = 2ull * x.W * x.ld; sa.stride[2] = 2ull * x.H * x.W * x.ld;
@@ -626,6 +660,7 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o) {
   p.n_tiles = ceil_div(gemm_n, p.BN);
   sb.box[0] = 64; sb.box[1] = p.BN; sb.box[2] = 1; sb.box[3] = 1; sb.box[4] = 1;
   p.num_taps = taps;
+  p.nprim = taps;
   p.idesc = make_idesc(dtype, p.BN);
   p.ocol = 1;
   p.out_fp32 = o.out_fp32 ? 1 : 0;
@@ -687,14 +722,17 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o) {
     p.tap_src[t2] = 1;
     p.tap_kc[t2] = ceil_div(o.x2->C, 64);
     p.num_taps = taps + 1;
-    k2 = o.w2->cin;
+    k2 = o.x2_identity ? 0 : o.w2->cin;
   }
   {
     const double m_valid = 1.0 * x.N * Ho * Wo, k_valid = 1.0 * taps * w.cin + k2;
     const double bytes = 2.0 * (1.0 * x.N * x.H * x.W * w.cin + m_valid * outc * (o.out_fp32 ? 2 : 1) + 1.0 * gemm_n * k_valid +
                                 (o.res ? m_valid * outc : 0) + m_valid * k2);
     const char* kind = sub ? "tapgemm:conv_up2x" : (k == 3) ? (o.stride == 2 ? "tapgemm:conv3x3s2" : "tapgemm:conv3x3") : "tapgemm:linear";
-    launch_gemm(P, sa, sb, p, o.to_io_out_nchw, kind, k_valid, bytes, o.x2 ? &sa2 : nullptr, o.x2 ? &sb2 : nullptr);
+    TmapSpec sh = sa;
+    sh.box[1] = TG2_HALO_W; sh.box[2] = TG2_HALO_H; sh.box[3] = 1;
+    launch_gemm(P, sa, sb, p, o.to_io_out_nchw, kind, k_valid, bytes, o.x2 ? &sa2 : nullptr, o.x2 ? &sb2 : nullptr,
+                want_halo ? &sh : nullptr);
   }
   return out;
 }

@@ -94,6 +94,7 @@ struct ConvOpts {
   // second source folded into the same accumulator: out = conv(x) + conv1x1(x2)   (resnet conv_shortcut, decoder skip convs)
   const Act* x2 = nullptr;
   const PW* w2 = nullptr;
+  bool x2_identity = false;      // x2/w2 is the residual x identity trick: not algorithmic work (excluded from flop counts)
   int subpixel_phase = -1;       // >=0: this launch is parity phase (py*2+px) of a fused nearest-2x-upsample + 3x3 conv
 };
 
@@ -142,6 +143,7 @@ class Engine {
           float scale = 1.f, const float* bias_add = nullptr);
   PW prep_twin(const std::string& pre, const std::string& cur, float r);
   PW prep_im2col3(const std::string& name);
+  PW prep_identity(int n);                                          // [n][n] identity as a 1x1 'weight'
   PW prep_subpixel(const std::string& name);                       // 16 pre-summed 2x2 taps for upsample2x+conv3x3
   Act conv_up2x(Plan& P, const Act& x, const PW& wsub, const Act* x2, const PW* w2);                        // 3x3 conv over 3 channels as a K=32 single-tap GEMM
   NormW norm(const std::string& name);
@@ -166,8 +168,9 @@ class Engine {
   }
   // encodes the tensor maps and appends the launch; picks the CTA-pair kernel (tapgemm2) for big conv/linear layers
   void launch_gemm(Plan& P, const TmapSpec& sa, TmapSpec sb, const TapGemmParams& p, bool out_from_io, const char* kind,
-                   double k_valid, double bytes, const TmapSpec* sa2 = nullptr, const TmapSpec* sb2 = nullptr);
-  bool use_pair = true;
+                   double k_valid, double bytes, const TmapSpec* sa2 = nullptr, const TmapSpec* sb2 = nullptr,
+                   const TmapSpec* shalo = nullptr);
+  bool use_pair = true, use_halo = true, use_idres = true;
   std::string profile_json(int reps, cudaStream_t st);
   int pick_bn(long long m_tiles, int N, bool even32) const;
 

@@ -422,6 +422,13 @@ __global__ void wprep_store_im2col_kernel(const float* __restrict__ acc, T* __re
   if (k < 27) { const int t = k / 3, c = k % 3; v = acc[(o * 3 + c) * 9 + t]; }
   out[i] = Elem<T>::from_f(v);
 }
+// identity matrix [n][n] (K-major rows) in the activation dtype: the residual of a 3x3 conv rides the GEMM as one more K-slab
+template <typename T>
+__global__ void identity_store_kernel(T* __restrict__ out, int n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(n) * n) return;
+  out[i] = Elem<T>::from_f((i / n) == (i % n) ? 1.f : 0.f);
+}
 static __global__ void bias_store_kernel(const float* __restrict__ b, float* __restrict__ out, int cout, int row_off,
                                   int interleave_half, const float* __restrict__ add) {
   const int o = blockIdx.x * blockDim.x + threadIdx.x;

@@ -8,10 +8,10 @@
 // out-of-bounds zero fill, never from materialised copies.
 //
 // sm_100a structure (one persistent CTA per SM, 192 threads):
-//   warp 4 lane 0 : TMA producer   cp.async.bulk.tensor.5d -> 128B-swizzled smem ring (4 stages)
-//   warp 5 lane 0 : MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN<=256, K=16
+//   warp 8        : TMA producer   cp.async.bulk.tensor.5d -> 128B-swizzled smem ring (4 stages)
+//   warp 9        : MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN<=256, K=16
 //                                  accumulators in TMEM (2 stages x 256 fp32 columns)
-//   warps 0..3    : epilogue       tcgen05.ld 32x32b -> bias/residual/GEGLU/clamp -> global
+//   warps 0..7    : epilogue       tcgen05.ld 32x32b -> bias/residual/GEGLU/clamp -> global
 //   mbarriers     : full/empty per smem stage, tmem_full/tmem_empty per accumulator stage
 //
 // Replaces (reference call sites): every nn.Conv2d / nn.Linear / SDPA matmul under
@@ -31,7 +31,8 @@ constexpr int TG_B_STAGE = 256 * TG_BK * 2;      // 32 KiB (BN <= 256)
 constexpr int TG_BAR_BYTES = 256;
 constexpr int TG_BIAS_BYTES = 2 * 256 * 4;       // per-tile bias slice, double-buffered like the accumulators
 constexpr int TG_SMEM = TG_STAGES * (TG_A_STAGE + TG_B_STAGE) + TG_BAR_BYTES + TG_BIAS_BYTES + 1024;  // +1024: manual alignment
-constexpr int TG_THREADS = 192;
+constexpr int TG_EPI_WARPS = 8;        // two warps per TMEM lane quarter: they alternate 32-column rounds
+constexpr int TG_THREADS = (TG_EPI_WARPS + 2) * 32;   // + TMA producer warp + MMA issuer warp
 constexpr int TG_ACC_COLS = 256;       // TMEM columns per accumulator stage
 
 enum TgAct : int { TG_ACT_NONE = 0, TG_ACT_CLAMP1 = 1, TG_ACT_GEGLU = 2 };
@@ -48,6 +49,9 @@ struct TapGemmParams {
   int num_taps, kchunks;   // kchunks: default K chunks per tap (tap_kc overrides per tap)
   int tap_src[TG_MAX_TAPS]; // 0: (tmA, tmB)   1: (tmA2, tmB2) — a second activation tensor folded into the same accumulator
   int tap_kc[TG_MAX_TAPS];  // K chunks (of 64) for this tap
+  int nprim;                // the first nprim taps share kchunks and are walked k-chunk-outer / tap-inner (same
+                            // accumulation order in every kernel variant => bit-identical results); the rest follow
+  int halo;                 // pair kernel only: 3x3 taps read shifted views of ONE halo tile per k-chunk
   int tap_a[TG_MAX_TAPS][5];
   int tap_b[TG_MAX_TAPS][4];
   uint32_t idesc;
@@ -268,6 +272,7 @@ template <typename T>
 __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const TileCoord& c, int row, int warp, int j1, int j2,
                                               int j3, int j4, int acc, int aphase, uint32_t tmem_base, float* s_bias,
                                               uint32_t tfull_bar_addr) {
+  const int grp = warp >> 2;                     // which of the two warps sharing this TMEM lane quarter
   const int g1 = c.t[0] * p.box[0] + j1, g2 = c.t[1] * p.box[1] + j2, g3 = c.t[2] * p.box[2] + j3,
             g4 = c.t[3] * p.box[3] + j4;
   const bool row_ok = (g1 < p.ext[0]) && (g2 < p.ext[1]) && (g3 < p.ext[2]) && (g4 < p.ext[3]);
@@ -279,32 +284,42 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const Tile
   // stage this tile's bias slice in smem once (a per-chunk global load here stalled the whole epilogue: r01 ncu)
   float* sb = s_bias + acc * 256;
   if (p.bias_mode == TG_BIAS_COL) {
-    for (int cc = row; cc < p.BN; cc += 128) sb[cc] = (n0 + cc < p.N) ? p.bias[n0 + cc] : 0.f;
+    for (int cc = warp * 32 + (threadIdx.x & 31); cc < p.BN; cc += TG_EPI_WARPS * 32)
+      sb[cc] = (n0 + cc < p.N) ? p.bias[n0 + cc] : 0.f;
   }
-  asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+  asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps only
 
-  // Residual reads do not depend on the accumulator: round r+1's 32 columns are prefetched while round r is
-  // converted/stored, and round 0's before the accumulator wait, so global-load latency is off the per-tile path.
+  // Residual reads do not depend on the accumulator: this thread's WHOLE residual slice (its row x the 32-column rounds
+  // r = grp, grp+2, ...; <= 256 B) is requested before the accumulator wait, so global-load latency overlaps the mainloop
+  // (one round of lookahead left the epilogue latency-bound: 0.95 ms vs 0.60 ms for the same conv with/without residual).
   const int nrounds = (p.BN + 31) >> 5;
   const bool res_on = p.res != nullptr && row_ok && p.rcol == 1 && p.act != TG_ACT_GEGLU;
-  auto prefetch = [&](int r, uint4 (&dst)[4]) -> bool {
-    if (!res_on || r >= nrounds) return false;
-    const int colg = n0 + 32 * r;
-    const int nch = min(2, (p.BN - 32 * r) >> 4);
-    const T* rgrp = reinterpret_cast<const T*>(p.res) + rbase + colg;
-    if (colg + 16 * nch > p.N || (reinterpret_cast<uintptr_t>(rgrp) & 15) != 0) return false;
-    dst[0] = ld_nc16(rgrp); dst[1] = ld_nc16(rgrp + 8);
-    if (nch == 2) { dst[2] = ld_nc16(rgrp + 16); dst[3] = ld_nc16(rgrp + 24); }
-    return true;
-  };
-  uint4 rqa[4], rqb[4];
-  bool fa = prefetch(0, rqa), fb = false;
+  uint4 rq[4][4];
+  bool fast[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = grp + 2 * i;
+    fast[i] = false;
+    if (res_on && r < nrounds) {
+      const int colg = n0 + 32 * r;
+      const int nch = min(2, (p.BN - 32 * r) >> 4);
+      const T* rgrp = reinterpret_cast<const T*>(p.res) + rbase + colg;
+      if (colg + 16 * nch <= p.N && (reinterpret_cast<uintptr_t>(rgrp) & 15) == 0) {
+        rq[i][0] = ld_nc16(rgrp); rq[i][1] = ld_nc16(rgrp + 8);
+        if (nch == 2) { rq[i][2] = ld_nc16(rgrp + 16); rq[i][3] = ld_nc16(rgrp + 24); }
+        fast[i] = true;
+      }
+    }
+  }
 
   mbar_wait(tfull_bar_addr, aphase, p.err, 4);
   tc_fence_after();
-  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * TG_ACC_COLS;
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + acc * TG_ACC_COLS;
 
-  auto do_round = [&](int r, const uint4 (&rq)[4], bool rfast) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = grp + 2 * i;
+    if (r >= nrounds) break;                     // warp-uniform
     const int c0 = 32 * r;
     const int nch = min(2, (p.BN - c0) >> 4);
     uint32_t raw0[16], raw1[16];
@@ -312,19 +327,11 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const Tile
     tc_ld16(taddr + c0, raw0);
     if (nch == 2) tc_ld16(taddr + c0 + 16, raw1);
     tc_wait_ld();
-    if (!row_ok) return;
+    if (!row_ok) continue;
     const int col0 = n0 + c0;
-    if (col0 < p.N) epilogue_chunk<T>(p, raw0, col0, obase, rbase, rbias, sb + c0, rfast, rq[0], rq[1]);
+    if (col0 < p.N) epilogue_chunk<T>(p, raw0, col0, obase, rbase, rbias, sb + c0, fast[i], rq[i][0], rq[i][1]);
     if (nch == 2 && col0 + 16 < p.N)
-      epilogue_chunk<T>(p, raw1, col0 + 16, obase, rbase, rbias, sb + c0 + 16, rfast, rq[2], rq[3]);
-  };
-  for (int r = 0; r < nrounds; r += 2) {
-    fb = prefetch(r + 1, rqb);
-    do_round(r, rqa, fa);
-    if (r + 1 < nrounds) {
-      fa = prefetch(r + 2, rqa);
-      do_round(r + 1, rqb, fb);
-    }
+      epilogue_chunk<T>(p, raw1, col0 + 16, obase, rbase, rbias, sb + c0 + 16, fast[i], rq[i][2], rq[i][3]);
   }
 }
 
@@ -350,16 +357,16 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   int steps = 0;
   for (int t = 0; t < p.num_taps; ++t) steps += p.tap_kc[t];
 
-  if (warp == 4 && lane == 0) {
+  if (warp == TG_EPI_WARPS && lane == 0) {
     for (int s = 0; s < TG_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TG_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA2)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB2)) : "memory");
   }
-  if (warp == 5) {
+  if (warp == TG_EPI_WARPS + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -369,7 +376,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-  if (warp == 4) {
+  if (warp == TG_EPI_WARPS) {
     // ================================ TMA producer (whole warp runs the loop, one elected lane issues) ==========
     int stage = 0, phase = 0;
     const uint32_t tx_bytes = TG_A_STAGE + static_cast<uint32_t>(p.BN) * (TG_BK * 2);
@@ -379,25 +386,26 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 a4 = c.t[3] * p.a_mul[3];
       const int b2 = c.t[1] * p.b_mul[0], b3 = c.t[2] * p.b_mul[1], b4 = c.t[3] * p.b_mul[2];
       const int n0 = c.nt * p.BN;
-      for (int t = 0; t < p.num_taps; ++t) {
+      auto load_step = [&](int t, int kc) {
         const CUtensorMap* ta = p.tap_src[t] ? &tmA2 : &tmA;
         const CUtensorMap* tb = p.tap_src[t] ? &tmB2 : &tmB;
-        const int nkc = p.tap_kc[t];
-        for (int kc = 0; kc < nkc; ++kc) {
-          mbar_wait(empty_bar(stage), phase ^ 1, p.err, 1);
-          if (elect_one()) {
-            mbar_expect_tx(full_bar(stage), tx_bytes);
-            tma_load_5d(sA + stage * TG_A_STAGE, ta, full_bar(stage), kc * TG_BK + p.tap_a[t][0],
-                        a1 + p.tap_a[t][1], a2 + p.tap_a[t][2], a3 + p.tap_a[t][3], a4 + p.tap_a[t][4]);
-            tma_load_5d(sB + stage * TG_B_STAGE, tb, full_bar(stage), kc * TG_BK + p.tap_b[t][0], n0,
-                        b2 + p.tap_b[t][1], b3 + p.tap_b[t][2], b4 + p.tap_b[t][3]);
-          }
-          __syncwarp();
-          if (++stage == TG_STAGES) { stage = 0; phase ^= 1; }
+        mbar_wait(empty_bar(stage), phase ^ 1, p.err, 1);
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(stage), tx_bytes);
+          tma_load_5d(sA + stage * TG_A_STAGE, ta, full_bar(stage), kc * TG_BK + p.tap_a[t][0],
+                      a1 + p.tap_a[t][1], a2 + p.tap_a[t][2], a3 + p.tap_a[t][3], a4 + p.tap_a[t][4]);
+          tma_load_5d(sB + stage * TG_B_STAGE, tb, full_bar(stage), kc * TG_BK + p.tap_b[t][0], n0,
+                      b2 + p.tap_b[t][1], b3 + p.tap_b[t][2], b4 + p.tap_b[t][3]);
         }
-      }
+        __syncwarp();
+        if (++stage == TG_STAGES) { stage = 0; phase ^= 1; }
+      };
+      for (int kc = 0; kc < p.kchunks; ++kc)
+        for (int t = 0; t < p.nprim; ++t) load_step(t, kc);
+      for (int t = p.nprim; t < p.num_taps; ++t)
+        for (int kc = 0; kc < p.tap_kc[t]; ++kc) load_step(t, kc);
     }
-  } else if (warp == 5) {
+  } else if (warp == TG_EPI_WARPS + 1) {
     // ================================ MMA issuer (warp-uniform loop, elected lane issues) ================================
     int stage = 0, phase = 0, iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
@@ -422,8 +430,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ================================ epilogue (warps 0..3) ================================
-    const int row = warp * 32 + lane;
+    // ================================ epilogue (warps 0..7) ================================
+    const int row = (warp & 3) * 32 + lane;
     int rr = row;
     const int j1 = rr % p.box[0]; rr /= p.box[0];
     const int j2 = rr % p.box[1]; rr /= p.box[1];
@@ -442,7 +450,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == TG_EPI_WARPS + 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }

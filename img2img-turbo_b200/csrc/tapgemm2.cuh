@@ -16,7 +16,16 @@ namespace i2it {
 
 constexpr int TG2_STAGES = 6;
 constexpr int TG2_B_STAGE = 128 * TG_BK * 2;     // half of a BN<=256 weight tile: 16 KiB
-constexpr int TG2_SMEM = TG2_STAGES * (TG_A_STAGE + TG2_B_STAGE) + TG_BAR_BYTES + TG_BIAS_BYTES + 1024;
+// halo mode (3x3 stride-1 convs): ONE halo tile per k-chunk instead of nine shifted 128-row boxes.  Output tile = 8 wide x 16
+// tall; the halo box is 18 rows x 16 pixels (8 + 2 halo + 6 unused, so that every image row starts a 2048-byte group and the
+// 128B-swizzle phase of a tap's view is the same for all of its 8-row groups: base_offset = dx).
+constexpr int TG2_HALO_W = 16, TG2_HALO_H = 18;
+constexpr int TG2_HALO_BYTES = TG2_HALO_H * TG2_HALO_W * TG_BK * 2;   // 36,864
+constexpr int TG2_HALO_STAGES = 3;
+constexpr int TG2_DATA_BYTES = (TG2_STAGES * (TG_A_STAGE + TG2_B_STAGE) > TG2_HALO_STAGES * TG2_HALO_BYTES + TG2_STAGES * TG2_B_STAGE)
+                                   ? TG2_STAGES * (TG_A_STAGE + TG2_B_STAGE)
+                                   : TG2_HALO_STAGES * TG2_HALO_BYTES + TG2_STAGES * TG2_B_STAGE;
+constexpr int TG2_SMEM = TG2_DATA_BYTES + TG_BAR_BYTES + TG_BIAS_BYTES + 1024;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -60,6 +69,17 @@ __device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
       ::"r"(bar) : "memory");
 }
 
+// descriptor of a tap's view into the halo tile: rows of 128 B, 8-row groups 2048 B apart (one image row of the 16-pixel
+// pitch), swizzle phase of the first row = dx (start is dx rows past a 1024-byte boundary)
+__device__ __forceinline__ uint64_t umma_desc_halo(uint32_t saddr, uint32_t dx) {
+  uint64_t d = static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(2048 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(dx & 7) << 49;      // base_offset
+  d |= static_cast<uint64_t>(2) << 61;           // SWIZZLE_128B
+  return d;
+}
+
 // host: instruction descriptor for the pair MMA (M = 256)
 inline uint32_t make_idesc2(int dtype, int bn) {
   uint32_t fmt = (dtype == DT_BF16) ? 1u : 0u;
@@ -71,17 +91,20 @@ template <typename T>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
-                const __grid_constant__ TapGemmParams p) {
+                const __grid_constant__ CUtensorMap tmH, const __grid_constant__ TapGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // normal mode: [A stages][B stages]; halo mode: [halo stages][B stages]
   const uint32_t sA = base;
-  const uint32_t sB = base + TG2_STAGES * TG_A_STAGE;
-  const uint32_t bars = sB + TG2_STAGES * TG2_B_STAGE;
+  const uint32_t sB = base + (p.halo ? TG2_HALO_STAGES * TG2_HALO_BYTES : TG2_STAGES * TG_A_STAGE);
+  const uint32_t bars = base + TG2_DATA_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (TG2_STAGES + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * TG2_STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * TG2_STAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * TG2_STAGES + 4);
+  auto hfull_bar = [&](int s) { return bars + 8u * (2 * TG2_STAGES + 6 + s); };
+  auto hempty_bar = [&](int s) { return bars + 8u * (2 * TG2_STAGES + 6 + TG2_HALO_STAGES + s); };
   float* const s_bias = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + TG_BAR_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -106,17 +129,19 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     return c;
   };
 
-  if (warp == 4 && lane == 0) {
+  if (warp == TG_EPI_WARPS && lane == 0) {
     for (int s = 0; s < TG2_STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * TG_EPI_WARPS); }
+    for (int s = 0; s < TG2_HALO_STAGES; ++s) { mbar_init(hfull_bar(s), 2); mbar_init(hempty_bar(s), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA2)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB2)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmH)) : "memory");
   }
   cluster_sync_all();                                   // peer barriers initialised before any remote arrive / TMEM alloc
-  if (warp == 5) {
+  if (warp == TG_EPI_WARPS + 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
@@ -126,64 +151,116 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-  if (warp == 4) {
+  if (warp == TG_EPI_WARPS) {
     // ================================ TMA producer (both CTAs) ================================
-    int stage = 0, phase = 0;
-    const uint32_t tx_bytes = 2u * (TG_A_STAGE + static_cast<uint32_t>(half_bn) * (TG_BK * 2));   // both CTAs' bytes
+    int stage = 0, phase = 0, hs = 0, hphase = 0;
+    const uint32_t b_bytes = static_cast<uint32_t>(half_bn) * (TG_BK * 2);
+    const uint32_t tx_bytes = 2u * (TG_A_STAGE + b_bytes);                                         // both CTAs' bytes
     for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
       const TileCoord c = decode_pair(pt);
       const int a1 = c.t[0] * p.a_mul[0], a2 = c.t[1] * p.a_mul[1], a3 = c.t[2] * p.a_mul[2], a4 = c.t[3] * p.a_mul[3];
-      // B batch-like coordinates follow the LEADER's tile (identical for conv/linear where b_mul == 0)
       const int b2 = c.t[1] * p.b_mul[0], b3 = c.t[2] * p.b_mul[1], b4 = c.t[3] * p.b_mul[2];
       const int n0 = c.nt * p.BN + static_cast<int>(rank) * half_bn;
-      for (int t = 0; t < p.num_taps; ++t) {
+      auto load_step = [&](int t, int kc) {
         const CUtensorMap* ta = p.tap_src[t] ? &tmA2 : &tmA;
         const CUtensorMap* tb = p.tap_src[t] ? &tmB2 : &tmB;
-        const int nkc = p.tap_kc[t];
-        for (int kc = 0; kc < nkc; ++kc) {
-          mbar_wait(empty_bar(stage), phase ^ 1, p.err, 21);
+        mbar_wait(empty_bar(stage), phase ^ 1, p.err, 21);
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(full_bar(stage), tx_bytes);
+          else mbar_arrive_cluster(full_bar(stage), 0);
+          tma_load_5d_2sm(sA + stage * TG_A_STAGE, ta, full_bar(stage), kc * TG_BK + p.tap_a[t][0], a1 + p.tap_a[t][1],
+                          a2 + p.tap_a[t][2], a3 + p.tap_a[t][3], a4 + p.tap_a[t][4]);
+          tma_load_5d_2sm(sB + stage * TG2_B_STAGE, tb, full_bar(stage), kc * TG_BK + p.tap_b[t][0], n0,
+                          b2 + p.tap_b[t][1], b3 + p.tap_b[t][2], b4 + p.tap_b[t][3]);
+        }
+        __syncwarp();
+        if (++stage == TG2_STAGES) { stage = 0; phase ^= 1; }
+      };
+      if (p.halo) {
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          // one halo tile (rows y0-1 .. y0+16, pixels x0-1 .. x0+14) serves all nine taps of this k-chunk
+          mbar_wait(hempty_bar(hs), hphase ^ 1, p.err, 24);
           if (elect_one()) {
-            if (leader) mbar_expect_tx(full_bar(stage), tx_bytes);
-            else mbar_arrive_cluster(full_bar(stage), 0);
-            tma_load_5d_2sm(sA + stage * TG_A_STAGE, ta, full_bar(stage), kc * TG_BK + p.tap_a[t][0], a1 + p.tap_a[t][1],
-                            a2 + p.tap_a[t][2], a3 + p.tap_a[t][3], a4 + p.tap_a[t][4]);
-            tma_load_5d_2sm(sB + stage * TG2_B_STAGE, tb, full_bar(stage), kc * TG_BK + p.tap_b[t][0], n0,
-                            b2 + p.tap_b[t][1], b3 + p.tap_b[t][2], b4 + p.tap_b[t][3]);
+            if (leader) mbar_expect_tx(hfull_bar(hs), 2u * TG2_HALO_BYTES);
+            else mbar_arrive_cluster(hfull_bar(hs), 0);
+            tma_load_5d_2sm(sA + hs * TG2_HALO_BYTES, &tmH, hfull_bar(hs), kc * TG_BK, a1 - 1, a2 - 1, a3, a4);
           }
           __syncwarp();
-          if (++stage == TG2_STAGES) { stage = 0; phase ^= 1; }
+          if (++hs == TG2_HALO_STAGES) { hs = 0; hphase ^= 1; }
+          for (int t = 0; t < p.nprim; ++t) {
+            mbar_wait(empty_bar(stage), phase ^ 1, p.err, 21);
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(full_bar(stage), 2u * b_bytes);
+              else mbar_arrive_cluster(full_bar(stage), 0);
+              tma_load_5d_2sm(sB + stage * TG2_B_STAGE, &tmB, full_bar(stage), kc * TG_BK + p.tap_b[t][0], n0,
+                              b2 + p.tap_b[t][1], b3 + p.tap_b[t][2], b4 + p.tap_b[t][3]);
+            }
+            __syncwarp();
+            if (++stage == TG2_STAGES) { stage = 0; phase ^= 1; }
+          }
         }
+      } else {
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          for (int t = 0; t < p.nprim; ++t) load_step(t, kc);
+        for (int t = p.nprim; t < p.num_taps; ++t)
+          for (int kc = 0; kc < p.tap_kc[t]; ++kc) load_step(t, kc);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == TG_EPI_WARPS + 1) {
     // ================================ MMA issuer (leader CTA only) ================================
     if (leader) {
-      int stage = 0, phase = 0, iter = 0;
+      int stage = 0, phase = 0, iter = 0, hs = 0, hphase = 0;
       for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++iter) {
         const int acc = iter & 1, aphase = (iter >> 1) & 1;
         mbar_wait(tempty_bar(acc), aphase ^ 1, p.err, 22);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * TG_ACC_COLS;
-        for (int s = 0; s < steps; ++s) {
-          mbar_wait(full_bar(stage), phase, p.err, 23);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint64_t adesc = umma_desc_sw128(sA + stage * TG_A_STAGE);
-            const uint64_t bdesc = umma_desc_sw128(sB + stage * TG2_B_STAGE);
+        if (p.halo) {
+          int s = 0;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(hfull_bar(hs), hphase, p.err, 25);
+            for (int t = 0; t < p.nprim; ++t, ++s) {
+              mbar_wait(full_bar(stage), phase, p.err, 23);
+              tc_fence_after();
+              if (elect_one()) {
+                // tap (dy,dx) = rows shifted by dy image rows (2048 B) and dx pixels (128 B) inside the halo tile
+                const uint32_t dy = static_cast<uint32_t>(p.tap_a[t][2] + 1), dx = static_cast<uint32_t>(p.tap_a[t][1] + 1);
+                const uint64_t adesc = umma_desc_halo(sA + hs * TG2_HALO_BYTES + dy * 2048u + dx * 128u, dx);
+                const uint64_t bdesc = umma_desc_sw128(sB + stage * TG2_B_STAGE);
 #pragma unroll
-            for (int k = 0; k < TG_BK / 16; ++k)
-              tc_mma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (s > 0 || k > 0) ? 1u : 0u);
-            tc_commit_2sm(empty_bar(stage));
-            if (s == steps - 1) tc_commit_2sm(tfull_bar(acc));
+                for (int k = 0; k < TG_BK / 16; ++k)
+                  tc_mma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (s > 0 || k > 0) ? 1u : 0u);
+                tc_commit_2sm(empty_bar(stage));
+                if (t == p.nprim - 1) tc_commit_2sm(hempty_bar(hs));
+                if (s == steps - 1) tc_commit_2sm(tfull_bar(acc));
+              }
+              __syncwarp();
+              if (++stage == TG2_STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++hs == TG2_HALO_STAGES) { hs = 0; hphase ^= 1; }
           }
-          __syncwarp();
-          if (++stage == TG2_STAGES) { stage = 0; phase ^= 1; }
+        } else {
+          for (int s = 0; s < steps; ++s) {
+            mbar_wait(full_bar(stage), phase, p.err, 23);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t adesc = umma_desc_sw128(sA + stage * TG_A_STAGE);
+              const uint64_t bdesc = umma_desc_sw128(sB + stage * TG2_B_STAGE);
+#pragma unroll
+              for (int k = 0; k < TG_BK / 16; ++k)
+                tc_mma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (s > 0 || k > 0) ? 1u : 0u);
+              tc_commit_2sm(empty_bar(stage));
+              if (s == steps - 1) tc_commit_2sm(tfull_bar(acc));
+            }
+            __syncwarp();
+            if (++stage == TG2_STAGES) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
   } else {
     // ================================ epilogue (both CTAs, own 128 rows) ================================
-    const int row = warp * 32 + lane;
+    const int row = (warp & 3) * 32 + lane;
     int rr = row;
     const int j1 = rr % p.box[0]; rr /= p.box[0];
     const int j2 = rr % p.box[1]; rr /= p.box[1];
@@ -203,7 +280,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                                   // nobody leaves (or frees TMEM) while the peer may still signal it
-  if (warp == 5) {
+  if (warp == TG_EPI_WARPS + 1) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }

@@ -164,6 +164,8 @@ CASES = {
     # big enough (>= 2 x 148 tiles) to take the CTA-pair (cta_group::2) kernel
     "pair_conv": lambda: case_conv(bf, 4, 128, 128, 128, 128, res=True),
     "pair_conv256": lambda: case_conv(hf, 2, 128, 128, 256, 256),
+    "halo_ragged": lambda: case_conv(bf, 16, 40, 40, 64, 512, res=True),
+    "halo_k320": lambda: case_conv(hf, 8, 64, 64, 320, 320),
     "pair_lin": lambda: case_linear(bf, 65536, 320, 320, res=True),
     "pair_lin_odd": lambda: case_linear(hf, 128 * 301 + 17, 256, 512),
     "pair_geglu": lambda: case_conv(bf, 1, 1, 32768, 320, 2560, k=1, act=i2it.ACT_GEGLU),
