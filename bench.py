@@ -142,7 +142,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=512)
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--dtype", default=None, choices=["bf16", "fp16"])
+    ap.add_argument("--model", default="pix2pix", choices=["pix2pix", "cyclegan"],
+                    help="pix2pix = BASELINE config #2 (default, the headline); cyclegan = config #3 (day_to_night a2b, fp16, batch 16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default="", help="write the per-launch timing table (JSON) here")
     args = ap.parse_args()
@@ -160,18 +162,33 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.dtype is None:
+        args.dtype = "bf16" if args.model == "pix2pix" else "fp16"
+    if args.model == "cyclegan" and args.batch == 8:
+        args.batch = 16
     dt = torch.bfloat16 if args.dtype == "bf16" else torch.float16
     B, S, K, Wm = args.batch, args.size, args.steps, max(args.warmup, 3)
+    workload = WORKLOAD if args.model == "pix2pix" else "cyclegan-turbo day_to_night (a2b) fp16 batch=16/GPU 512x512 (BASELINE config #3)"
 
     # ---- model through the public (reference-compatible) API: random init, LoRA folded at load ----
     torch.manual_seed(0)
-    model = Pix2Pix_Turbo()                      # pretrained_name=None, pretrained_path=None -> random init (reference :131)
-    model.set_eval()
-    model.to(dt)
     prompt = "a synthetic benchmark prompt"
     c_t, text, eps = synthetic_inputs(B, S, 1024, dt, "cuda", seed_offset=rank)
+    if args.model == "pix2pix":
+        model = Pix2Pix_Turbo()                  # pretrained_name=None, pretrained_path=None -> random init (reference :131)
+        model.set_eval()
+        model.to(dt)
+        call = lambda x, **kw: model(x, prompt, **kw)
+    else:
+        from cyclegan_turbo import CycleGAN_Turbo
+        model = CycleGAN_Turbo(synthetic_caption="driving in the night", synthetic_direction="a2b")
+        model.eval()
+        model.to(dt)
+        prompt = model.caption
+        c_t = (c_t.float() * 0 + torch.rand(c_t.shape, generator=torch.Generator().manual_seed(1 + rank)).to("cuda") * 2 - 1).to(dt)
+        call = lambda x, **kw: model(x, **kw)
     with torch.no_grad():
-        out = model(c_t, prompt, eps=eps)        # builds engine + plan, caches the prompt embedding
+        out = call(c_t, eps=eps)                 # builds engine + plan, caches the prompt embedding
     eng = model._get_engine()
     text_emb = model._encode_text(prompt)
     torch.cuda.synchronize()
@@ -213,16 +230,19 @@ def main():
     # ---- e2e: the call a user makes (model(c_t, prompt)) with pinned-host input and a device->host read of the result ----
     host_in = synthetic_inputs(B, S, 1024, dt, None, seed_offset=rank)[0].pin_memory()
     host_out = torch.empty(B, 3, S, S, dtype=dt).pin_memory()
+    gathered_img = torch.empty(world * B, 3, S, S, device="cuda", dtype=dt) if world > 1 else None
     with torch.no_grad():
         for _ in range(2):
-            host_out.copy_(model(host_in.cuda(non_blocking=True), prompt), non_blocking=True)
+            host_out.copy_(call(host_in.cuda(non_blocking=True)), non_blocking=True)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         for _ in range(K):
             flush.zero_()
-            y = model(host_in.cuda(non_blocking=True), prompt)      # H2D + randn(eps) + path
+            y = call(host_in.cuda(non_blocking=True))               # H2D + randn(eps) + path (the call a user makes)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered_img, y)        # sharded users gather the images (dist.sharded_forward)
             host_out.copy_(y, non_blocking=True)                    # D2H of the step's result
             torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / K
@@ -253,11 +273,17 @@ def main():
     tg_ms, tg_fl = sum(p["ms"] for p in tg), sum(p["flops"] for p in tg)
     all_ms = sum(p["ms"] for p in prof)
     achieved = tg_fl / (tg_ms * 1e-3) / 1e12 if tg_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "tapgemm_kernel (tcgen05 implicit GEMM: conv3x3/1x1/linear/attention)",
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "tapgemm_dram_traffic.json")     # from the committed ncu capture of this command
+    if os.path.exists(tpath) and args.model == "pix2pix" and B == 8 and S == 512:
+        traffic = json.load(open(tpath)).get("dram_bytes_per_step")
+    roofline = {"bound": "tensor", "kernel": "tapgemm_kernel + tapgemm2_kernel (tcgen05 implicit GEMM: conv3x3/1x1/linear/attention; "
+                                             "all launches of a step, CTA-pair variant for the large layers)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "peak_source": peak_src,
                 "launches_per_step": len(tg), "avg_launch_ms": tg_ms / max(1, len(tg)),
                 "share_of_step": tg_ms / all_ms if all_ms else None,
-                "traffic": None,
+                "traffic": traffic, "traffic_note": "sum of dram__bytes_read+write over the step's tapgemm launches (ncu, profiles/)",
+                "algorithmic_bytes": sum(p["bytes"] for p in tg),
                 "step_tensor_frac": (B * FLOPS_PER_IMAGE / (ms_step * 1e-3)) / 1e12 / peak_tf,
                 "by_kind_ms": {k: round(v["ms"], 4) for k, v in sorted(by_kind.items(), key=lambda kv: -kv[1]["ms"])},
                 "hbm_kernels_gbs": {k: round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) for k, v in by_kind.items()
@@ -265,14 +291,14 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        ips, sec = cpu_oracle_images_per_s(model._sd, S, 1, 0, 1024, W.SD_TURBO)
-        cpu = {"value": ips, "unit": "images/s", "cores": CPU_THREADS, "kind": "port",
+        ips, sec = cpu_oracle_images_per_s(model._sd, S, 1, 0, 1024, W.SD_TURBO) if args.model == "pix2pix" else (None, 0.0)
+        cpu = None if ips is None else {"value": ips, "unit": "images/s", "cores": CPU_THREADS, "kind": "port",
                "sample": f"1 x one {S}x{S} image (batch 1), oracle fp32 restatement of the diffusers path, {sec:.1f} s"}
 
     line = {"metric": "512x512 images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": world * B, "size": S,
+            "config": {"workload": workload, "per_gpu_batch": B, "global_batch": world * B, "size": S,
                        "parallelism": f"dp{world}", "l2": "256 MiB flush write between timed iterations",
                        "collective": "1 x all_gather_into_tensor(output latents) per step" if world > 1 else "none",
                        "cuda_graph": True},

@@ -493,6 +493,13 @@ void Engine::launch_gemm(Plan& P, const TmapSpec& sa, TmapSpec sb, const TapGemm
   TmapSpec sb2 = sb2p ? *sb2p : sb;
   if (pair) { sb.box[1] = p.BN / 2; sb2.box[1] = p.BN / 2; p.idesc = make_idesc2(dtype, p.BN); }
   p.halo = (pair && shalo != nullptr && use_halo) ? 1 : 0;
+  {  // smem ring geometry: B stage = the real (half) tile rounded to the 1024-byte swizzle atom, as many stages as fit
+    const int brows = pair ? p.BN / 2 : p.BN;
+    p.b_stage = (brows * TG_BK * 2 + 1023) / 1024 * 1024;
+    const int budget = pair ? (p.halo ? TG2_DATA_BYTES - TG2_HALO_STAGES * TG2_HALO_BYTES : TG2_DATA_BYTES) : TG_STAGES * (TG_A_STAGE + TG_B_STAGE);
+    const int per = (p.halo ? 0 : TG_A_STAGE) + p.b_stage;
+    p.stages = std::max(2, std::min(TG_MAX_STAGES, budget / per));
+  }
   const CUtensorMap ta = encode_tmap(sa, dtype), tb = encode_tmap(sb, dtype);
   const CUtensorMap th = p.halo ? encode_tmap(*shalo, dtype) : ta;
   const CUtensorMap ta2 = sa2p ? encode_tmap(*sa2p, dtype) : ta, tb2 = sb2p ? encode_tmap(sb2, dtype) : tb;

@@ -165,23 +165,27 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc_fence_after();
       const uint32_t tS = tS0 + 64 * (j & 1);
       const int kbase = j * FA_BN;
-      const bool ragged = (kbase + FA_BN > p.Nk);
-      // pass 1: row max of the scaled logits
+      const bool ragged = (kbase + FA_BN > p.Nk);          // only the last KV tile; warp-uniform
+      const float sc = p.scale_log2e;
+      // pass 1: row max of the RAW logits (scale > 0 keeps the order; one FMNMX per element)
       float mx = -INFINITY;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t raw[32];
         tc_ld32(tS + lane_off + half * 32, raw);
         tc_wait_ld();
+        if (ragged) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float v = __uint_as_float(raw[i]) * p.scale_log2e;
-          if (ragged && kbase + half * 32 + i >= p.Nk) v = -INFINITY;
-          mx = fmaxf(mx, v);
+          for (int i = 0; i < 32; ++i)
+            if (kbase + half * 32 + i < p.Nk) mx = fmaxf(mx, __uint_as_float(raw[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
         }
       }
-      const float m_new = fmaxf(m, mx);
-      const float alpha = fast_exp2(m - m_new);      // first tile: exp2(-inf) = 0
+      const float m_new = fmaxf(m, mx);                    // m, m_new in raw (unscaled) units
+      const float alpha = fast_exp2((m - m_new) * sc);     // first tile: exp2(-inf) = 0
+      const float neg_ms = -m_new * sc;
       // fold in PV_{j-1} before P_{j-1}'s smem tile is overwritten
       if (j > 0) {
         mbar_wait(pv_full, (j - 1) & 1, p.err, 17);
@@ -195,7 +199,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           for (int i = 0; i < 32; ++i) o[half * 32 + i] = o[half * 32 + i] * alpha_prev + __uint_as_float(raw[i]);
         }
       }
-      // pass 2: p = exp2(s - m_new), row sum, pack to 16-bit, write the swizzled K-major P tile
+      // pass 2: p = exp2(s*scale - m*scale) (one FFMA + one MUFU per element), fp32 row sum of the unrounded p (as
+      // FlashAttention does), pack to 16 bit, write the swizzled K-major P tile
       float psum = 0.f;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -203,18 +208,23 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tc_ld32(tS + lane_off + half * 32, raw);
         tc_wait_ld();
         uint32_t pk[16];
+        if (ragged) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float v0 = __uint_as_float(raw[2 * i]) * p.scale_log2e, v1 = __uint_as_float(raw[2 * i + 1]) * p.scale_log2e;
-          if (ragged) {
-            if (kbase + half * 32 + 2 * i >= p.Nk) v0 = -INFINITY;
-            if (kbase + half * 32 + 2 * i + 1 >= p.Nk) v1 = -INFINITY;
+          for (int i = 0; i < 16; ++i) {
+            const int k0 = kbase + half * 32 + 2 * i;
+            const float p0 = (k0 < p.Nk) ? fast_exp2(fmaf(__uint_as_float(raw[2 * i]), sc, neg_ms)) : 0.f;
+            const float p1 = (k0 + 1 < p.Nk) ? fast_exp2(fmaf(__uint_as_float(raw[2 * i + 1]), sc, neg_ms)) : 0.f;
+            psum += p0 + p1;
+            pk[i] = Elem<T>::pack(p0, p1);
           }
-          const float p0 = fast_exp2(v0 - m_new), p1 = fast_exp2(v1 - m_new);
-          pk[i] = Elem<T>::pack(p0, p1);
-          // the sum uses the ROUNDED probabilities (what the PV GEMM will actually multiply), as SDPA does
-          const float2 pr = Elem<T>::unpack(pk[i]);
-          psum += pr.x + pr.y;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(raw[2 * i]), sc, neg_ms));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(raw[2 * i + 1]), sc, neg_ms));
+            psum += p0 + p1;
+            pk[i] = Elem<T>::pack(p0, p1);
+          }
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {               // 16-byte group g' = half*4+g holds keys 8g'..8g'+7 of this row

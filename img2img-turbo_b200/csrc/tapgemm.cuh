@@ -24,7 +24,8 @@ namespace i2it {
 
 constexpr int TG_BM = 128;             // rows per tile (= TMEM lanes)
 constexpr int TG_BK = 64;              // K elements per stage (= 128 B = one swizzle atom)
-constexpr int TG_STAGES = 4;
+constexpr int TG_STAGES = 4;            // stages when the B tile is the full 32 KiB; smaller tiles get more (<= TG_MAX_STAGES)
+constexpr int TG_MAX_STAGES = 8;
 constexpr int TG_MAX_TAPS = 16;
 constexpr int TG_A_STAGE = TG_BM * TG_BK * 2;    // 16 KiB
 constexpr int TG_B_STAGE = 256 * TG_BK * 2;      // 32 KiB (BN <= 256)
@@ -51,6 +52,7 @@ struct TapGemmParams {
   int tap_kc[TG_MAX_TAPS];  // K chunks (of 64) for this tap
   int nprim;                // the first nprim taps share kchunks and are walked k-chunk-outer / tap-inner (same
                             // accumulation order in every kernel variant => bit-identical results); the rest follow
+  int stages, b_stage;      // smem ring: number of stages and bytes per B stage (sized to the actual tile, <= 8 stages)
   int halo;                 // pair kernel only: 3x3 taps read shifted views of ONE halo tile per k-chunk
   int tap_a[TG_MAX_TAPS][5];
   int tap_b[TG_MAX_TAPS][4];
@@ -342,14 +344,16 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ TapGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int NS = p.stages;
+  const uint32_t BST = static_cast<uint32_t>(p.b_stage);
   const uint32_t sA = base;
-  const uint32_t sB = base + TG_STAGES * TG_A_STAGE;
-  const uint32_t bars = sB + TG_STAGES * TG_B_STAGE;
+  const uint32_t sB = base + NS * TG_A_STAGE;
+  const uint32_t bars = base + TG_STAGES * (TG_A_STAGE + TG_B_STAGE);
   auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (TG_STAGES + s); };
-  auto tfull_bar = [&](int a) { return bars + 8u * (2 * TG_STAGES + a); };
-  auto tempty_bar = [&](int a) { return bars + 8u * (2 * TG_STAGES + 2 + a); };
-  const uint32_t tmem_slot = bars + 8u * (2 * TG_STAGES + 4);
+  auto empty_bar = [&](int s) { return bars + 8u * (TG_MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * TG_MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * TG_MAX_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * TG_MAX_STAGES + 4);
   float* const s_bias = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + TG_BAR_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -358,7 +362,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   for (int t = 0; t < p.num_taps; ++t) steps += p.tap_kc[t];
 
   if (warp == TG_EPI_WARPS && lane == 0) {
-    for (int s = 0; s < TG_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < NS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TG_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -394,11 +398,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_expect_tx(full_bar(stage), tx_bytes);
           tma_load_5d(sA + stage * TG_A_STAGE, ta, full_bar(stage), kc * TG_BK + p.tap_a[t][0],
                       a1 + p.tap_a[t][1], a2 + p.tap_a[t][2], a3 + p.tap_a[t][3], a4 + p.tap_a[t][4]);
-          tma_load_5d(sB + stage * TG_B_STAGE, tb, full_bar(stage), kc * TG_BK + p.tap_b[t][0], n0,
+          tma_load_5d(sB + stage * BST, tb, full_bar(stage), kc * TG_BK + p.tap_b[t][0], n0,
                       b2 + p.tap_b[t][1], b3 + p.tap_b[t][2], b4 + p.tap_b[t][3]);
         }
         __syncwarp();
-        if (++stage == TG_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == NS) { stage = 0; phase ^= 1; }
       };
       for (int kc = 0; kc < p.kchunks; ++kc)
         for (int t = 0; t < p.nprim; ++t) load_step(t, kc);
@@ -418,7 +422,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         if (elect_one()) {
           const uint64_t adesc = umma_desc_sw128(sA + stage * TG_A_STAGE);
-          const uint64_t bdesc = umma_desc_sw128(sB + stage * TG_B_STAGE);
+          const uint64_t bdesc = umma_desc_sw128(sB + stage * BST);
 #pragma unroll
           for (int k = 0; k < TG_BK / 16; ++k)
             tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (s > 0 || k > 0) ? 1u : 0u);
@@ -426,7 +430,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (s == steps - 1) tc_commit(tfull_bar(acc));   // accumulator complete -> epilogue
         }
         __syncwarp();
-        if (++stage == TG_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == NS) { stage = 0; phase ^= 1; }
       }
     }
   } else {

@@ -95,16 +95,18 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   // normal mode: [A stages][B stages]; halo mode: [halo stages][B stages]
+  const int NS = p.stages;                                  // host-chosen: B stage sized to the real half tile, <= 8 stages
+  const uint32_t BST = static_cast<uint32_t>(p.b_stage);
   const uint32_t sA = base;
-  const uint32_t sB = base + (p.halo ? TG2_HALO_STAGES * TG2_HALO_BYTES : TG2_STAGES * TG_A_STAGE);
+  const uint32_t sB = base + (p.halo ? TG2_HALO_STAGES * TG2_HALO_BYTES : NS * TG_A_STAGE);
   const uint32_t bars = base + TG2_DATA_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (TG2_STAGES + s); };
-  auto tfull_bar = [&](int a) { return bars + 8u * (2 * TG2_STAGES + a); };
-  auto tempty_bar = [&](int a) { return bars + 8u * (2 * TG2_STAGES + 2 + a); };
-  const uint32_t tmem_slot = bars + 8u * (2 * TG2_STAGES + 4);
-  auto hfull_bar = [&](int s) { return bars + 8u * (2 * TG2_STAGES + 6 + s); };
-  auto hempty_bar = [&](int s) { return bars + 8u * (2 * TG2_STAGES + 6 + TG2_HALO_STAGES + s); };
+  auto empty_bar = [&](int s) { return bars + 8u * (TG_MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * TG_MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * TG_MAX_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * TG_MAX_STAGES + 4);
+  auto hfull_bar = [&](int s) { return bars + 8u * (2 * TG_MAX_STAGES + 6 + s); };
+  auto hempty_bar = [&](int s) { return bars + 8u * (2 * TG_MAX_STAGES + 6 + TG2_HALO_STAGES + s); };
   float* const s_bias = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + TG_BAR_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -130,7 +132,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   };
 
   if (warp == TG_EPI_WARPS && lane == 0) {
-    for (int s = 0; s < TG2_STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < NS; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * TG_EPI_WARPS); }
     for (int s = 0; s < TG2_HALO_STAGES; ++s) { mbar_init(hfull_bar(s), 2); mbar_init(hempty_bar(s), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -170,11 +172,11 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           else mbar_arrive_cluster(full_bar(stage), 0);
           tma_load_5d_2sm(sA + stage * TG_A_STAGE, ta, full_bar(stage), kc * TG_BK + p.tap_a[t][0], a1 + p.tap_a[t][1],
                           a2 + p.tap_a[t][2], a3 + p.tap_a[t][3], a4 + p.tap_a[t][4]);
-          tma_load_5d_2sm(sB + stage * TG2_B_STAGE, tb, full_bar(stage), kc * TG_BK + p.tap_b[t][0], n0,
+          tma_load_5d_2sm(sB + stage * BST, tb, full_bar(stage), kc * TG_BK + p.tap_b[t][0], n0,
                           b2 + p.tap_b[t][1], b3 + p.tap_b[t][2], b4 + p.tap_b[t][3]);
         }
         __syncwarp();
-        if (++stage == TG2_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == NS) { stage = 0; phase ^= 1; }
       };
       if (p.halo) {
         for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -192,11 +194,11 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (elect_one()) {
               if (leader) mbar_expect_tx(full_bar(stage), 2u * b_bytes);
               else mbar_arrive_cluster(full_bar(stage), 0);
-              tma_load_5d_2sm(sB + stage * TG2_B_STAGE, &tmB, full_bar(stage), kc * TG_BK + p.tap_b[t][0], n0,
+              tma_load_5d_2sm(sB + stage * BST, &tmB, full_bar(stage), kc * TG_BK + p.tap_b[t][0], n0,
                               b2 + p.tap_b[t][1], b3 + p.tap_b[t][2], b4 + p.tap_b[t][3]);
             }
             __syncwarp();
-            if (++stage == TG2_STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == NS) { stage = 0; phase ^= 1; }
           }
         }
       } else {
@@ -226,7 +228,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 // tap (dy,dx) = rows shifted by dy image rows (2048 B) and dx pixels (128 B) inside the halo tile
                 const uint32_t dy = static_cast<uint32_t>(p.tap_a[t][2] + 1), dx = static_cast<uint32_t>(p.tap_a[t][1] + 1);
                 const uint64_t adesc = umma_desc_halo(sA + hs * TG2_HALO_BYTES + dy * 2048u + dx * 128u, dx);
-                const uint64_t bdesc = umma_desc_sw128(sB + stage * TG2_B_STAGE);
+                const uint64_t bdesc = umma_desc_sw128(sB + stage * BST);
 #pragma unroll
                 for (int k = 0; k < TG_BK / 16; ++k)
                   tc_mma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (s > 0 || k > 0) ? 1u : 0u);
@@ -235,7 +237,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (s == steps - 1) tc_commit_2sm(tfull_bar(acc));
               }
               __syncwarp();
-              if (++stage == TG2_STAGES) { stage = 0; phase ^= 1; }
+              if (++stage == NS) { stage = 0; phase ^= 1; }
             }
             if (++hs == TG2_HALO_STAGES) { hs = 0; hphase ^= 1; }
           }
@@ -245,7 +247,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tc_fence_after();
             if (elect_one()) {
               const uint64_t adesc = umma_desc_sw128(sA + stage * TG_A_STAGE);
-              const uint64_t bdesc = umma_desc_sw128(sB + stage * TG2_B_STAGE);
+              const uint64_t bdesc = umma_desc_sw128(sB + stage * BST);
 #pragma unroll
               for (int k = 0; k < TG_BK / 16; ++k)
                 tc_mma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (s > 0 || k > 0) ? 1u : 0u);
@@ -253,7 +255,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               if (s == steps - 1) tc_commit_2sm(tfull_bar(acc));
             }
             __syncwarp();
-            if (++stage == TG2_STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == NS) { stage = 0; phase ^= 1; }
           }
         }
       }
