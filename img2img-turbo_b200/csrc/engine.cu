@@ -114,6 +114,7 @@ Engine::Engine(const i2it_config& c) : cfg(c), dtype(c.dtype) {
   I2IT_CUDA(cudaFuncSetAttribute(flash_attn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
   use_flash = std::getenv("I2IT_NO_FLASH") == nullptr;
   use_pair = std::getenv("I2IT_NO_PAIR") == nullptr;
+  pair_min_tiles = std::getenv("I2IT_PAIR_MIN_TILES") ? atoll(std::getenv("I2IT_PAIR_MIN_TILES")) : 2ll * num_sms;
   use_idres = std::getenv("I2IT_NO_IDRES") == nullptr;
   use_halo = std::getenv("I2IT_HALO") != nullptr;     // experimental (r01: descriptor semantics of shifted swizzled views unresolved -> wrong results); off by default
   I2IT_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG2_SMEM));
@@ -489,7 +490,7 @@ void Engine::launch_gemm(Plan& P, const TmapSpec& sa, TmapSpec sb, const TapGemm
   const long long total_tiles = m_tiles * p.n_tiles;
   // CTA-pair kernel: weights/B shared by every M tile (no per-tile B batch coordinates), enough tiles to fill the chip twice
   const bool pair = use_pair && p.b_mul[0] == 0 && p.b_mul[1] == 0 && p.b_mul[2] == 0 && (p.BN % 32) == 0 &&
-                    total_tiles >= 2ll * num_sms && m_tiles >= 2;
+                    total_tiles >= pair_min_tiles && m_tiles >= 2;
   TmapSpec sb2 = sb2p ? *sb2p : sb;
   if (pair) { sb.box[1] = p.BN / 2; sb2.box[1] = p.BN / 2; p.idesc = make_idesc2(dtype, p.BN); }
   p.halo = (pair && shalo != nullptr && use_halo) ? 1 : 0;

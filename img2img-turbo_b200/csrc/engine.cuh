@@ -171,6 +171,7 @@ class Engine {
                    double k_valid, double bytes, const TmapSpec* sa2 = nullptr, const TmapSpec* sb2 = nullptr,
                    const TmapSpec* shalo = nullptr);
   bool use_pair = true, use_halo = true, use_idres = true;
+  long long pair_min_tiles = 296;   // CTA-pair kernel from two waves of tiles upwards (tunable: I2IT_PAIR_MIN_TILES)
   std::string profile_json(int reps, cudaStream_t st);
   int pick_bn(long long m_tiles, int N, bool even32) const;
 

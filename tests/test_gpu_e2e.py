@@ -161,6 +161,30 @@ def test_public_api_cyclegan_batch():
     assert _err(yb, refb)[0] < 5e-3 and not torch.equal(y, yb)
 
 
+def test_non_square_resolution():
+    """H != W (multiples of 64): tile geometry, stride-2 views, sub-pixel phases and the NCHW writer on a 128x192 image."""
+    import oracle as O
+    import weights as W
+    cfg, dt = W.TINY, torch.bfloat16
+    sd = W.make_state_dict("pix2pix", cfg, seed=0, perturb_norm=True)
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(2, 1, 128, 192, generator=g) < 0.1).float().expand(-1, 3, -1, -1).contiguous()
+    text = torch.randn(1, 77, cfg["cross_dim"], generator=g)
+    eps = torch.randn(2, 4, 16, 24, generator=g)
+    q = lambda t: t.to(dt).float()
+    with torch.no_grad():
+        ref = O.pix2pix_forward(sd, q(x), q(text), q(eps), cfg)
+        ref16 = O.pix2pix_forward({k: v.to(dt) for k, v in sd.items()}, x.to(dt), text.to(dt), eps.to(dt), cfg)
+    e = _engine("pix2pix", cfg, dt, sd)
+    e.finalize(1.0, 1.0, 1.0, -1.0)
+    out = e.forward(x.to(dt).cuda(), text.to(dt).cuda(), eps.to(dt).cuda())
+    torch.cuda.synchronize()
+    m_ref, x_ref = _err(ref16, ref)
+    m, mx = _err(out, ref)
+    assert out.shape == (2, 3, 128, 192) and torch.isfinite(out.float()).all()
+    assert m <= 1.5 * m_ref + 2e-3 and mx <= 1.5 * x_ref + 5e-2, (m, m_ref, mx, x_ref)
+
+
 @pytest.fixture(scope="module")
 def full_model():
     import weights as W
