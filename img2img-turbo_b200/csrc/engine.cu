@@ -100,6 +100,8 @@ __global__ void cvt16_to_f32_kernel(const uint16_t* s, float* d, long long n, in
   else d[i] = __half2float(reinterpret_cast<const __half*>(s)[i]);
 }
 
+thread_local PdlState g_pdl;
+
 Engine::Engine(const i2it_config& c) : cfg(c), dtype(c.dtype) {
   I2IT_CHECK(c.dtype == DT_F16 || c.dtype == DT_BF16, "dtype must be I2IT_F16 or I2IT_BF16");
   I2IT_CUDA(cudaSetDevice(c.device));
@@ -114,6 +116,11 @@ Engine::Engine(const i2it_config& c) : cfg(c), dtype(c.dtype) {
   I2IT_CUDA(cudaFuncSetAttribute(flash_attn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
   use_flash = std::getenv("I2IT_NO_FLASH") == nullptr;
   use_pair = std::getenv("I2IT_NO_PAIR") == nullptr;
+  use_pdl = std::getenv("I2IT_PDL") != nullptr;     // programmatic dependent launch: measured neutral (1 CTA/SM kernels cannot co-reside), opt-in
+#ifdef I2IT_TRACE_BUILD
+  trace_on = std::getenv("I2IT_TRACE") != nullptr;
+#endif
+  use_ostage = std::getenv("I2IT_NO_OSTG") == nullptr;
   pair_min_tiles = std::getenv("I2IT_PAIR_MIN_TILES") ? atoll(std::getenv("I2IT_PAIR_MIN_TILES")) : 2ll * num_sms;
   use_idres = std::getenv("I2IT_NO_IDRES") == nullptr;
   use_halo = std::getenv("I2IT_HALO") != nullptr;     // experimental (r01: descriptor semantics of shifted swizzled views unresolved -> wrong results); off by default
@@ -517,25 +524,26 @@ void Engine::launch_gemm(Plan& P, const TmapSpec& sa, TmapSpec sb, const TapGemm
   char shp[160];
   snprintf(shp, sizeof shp, "M=%.0f N=%d K=%.0f taps=%d BN=%d tiles=%lld grid=%d%s", m_valid, p.N, k_valid, p.num_taps, p.BN,
            total_tiles, grid, pair ? (p.halo ? " pair halo" : " pair") : "");
+  // staged (coalesced) output stores pay off where the epilogue is the tile's critical path and the extra shared-memory
+  // pass is cheap: the 3x3 / sub-pixel convs with N <= 256 (measured: -7 % there, +5..15 % on the small-K linears / GEGLU)
+  p.ostage = (use_ostage && p.num_taps >= 5 && p.N <= 256) ? 1 : 0;
+  p.trace = nullptr;
+  if (trace_on) {   // diagnostic timeline (I2IT_TRACE=1): 16 clock64 stamps per CTA, dumped to stderr after each forward
+    p.trace = static_cast<unsigned long long*>(dmalloc(static_cast<size_t>(grid) * 16 * sizeof(unsigned long long)));
+    I2IT_CUDA(cudaMemset(p.trace, 0, static_cast<size_t>(grid) * 16 * sizeof(unsigned long long)));
+    P.traces.push_back({p.trace, grid, std::string(kind) + " " + shp});
+  }
   if (pair) {
     add_op(P, [ta, tb, ta2, tb2, th, p, grid, dt, out_from_io, plan](cudaStream_t st) {
       TapGemmParams q = p;
       if (out_from_io) q.out = plan->io.out;
-      cudaLaunchConfig_t cfg;
-      std::memset(&cfg, 0, sizeof cfg);
-      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TG_THREADS); cfg.dynamicSmemBytes = TG2_SMEM; cfg.stream = st;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-      if (dt == DT_BF16) cudaLaunchKernelEx(&cfg, tapgemm2_kernel<__nv_bfloat16>, ta, tb, ta2, tb2, th, q);
-      else cudaLaunchKernelEx(&cfg, tapgemm2_kernel<__half>, ta, tb, ta2, tb2, th, q);
+      DISPATCH_T(dt, (launch_k(tapgemm2_kernel<T>, dim3(grid), dim3(TG_THREADS), TG2_SMEM, st, 2, ta, tb, ta2, tb2, th, q)));
     }, kind, 2.0 * m_valid * p.N * k_valid, bytes, shp);
   } else {
     add_op(P, [ta, tb, ta2, tb2, p, grid, dt, out_from_io, plan](cudaStream_t st) {
       TapGemmParams q = p;
       if (out_from_io) q.out = plan->io.out;
-      DISPATCH_T(dt, (tapgemm_kernel<T><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, ta2, tb2, q)));
+      DISPATCH_T(dt, (launch_k(tapgemm_kernel<T>, dim3(grid), dim3(TG_THREADS), TG_SMEM, st, 0, ta, tb, ta2, tb2, q)));
     }, kind, 2.0 * m_valid * p.N * k_valid, bytes, shp);
   }
 }
@@ -779,13 +787,13 @@ Act Engine::group_norm(Plan& P, const Act& x, const NormW& nw, float eps, bool s
   const float* g = nw.g;
   const float* b = nw.b;
   add_op(P, [=](cudaStream_t st) {
-    DISPATCH_T(dt, (gn_stats_kernel<T><<<dim3(chunks, N), threads, static_cast<size_t>(rows) * 2 * C * sizeof(float), st>>>(
-                       reinterpret_cast<const T*>(xp), ximg, ldx, C, HW, cg, pix, d_part)));
+    DISPATCH_T(dt, (launch_k(gn_stats_kernel<T>, dim3(chunks, N), dim3(threads), static_cast<size_t>(rows) * 2 * C * sizeof(float), st, 0,
+                             reinterpret_cast<const T*>(xp), ximg, ldx, C, HW, cg, pix, d_part)));
   }, "gn_stats", 0, 2.0 * N * HW * C);
   const double inv_count = 1.0 / (static_cast<double>(HW) * cg);
-  add_op(P, [=](cudaStream_t st) { gn_finalize_kernel<<<N, 1024, 0, st>>>(d_part, chunks, inv_count, eps, d_stats); }, "gn_final");
+  add_op(P, [=](cudaStream_t st) { launch_k(gn_finalize_kernel, dim3(N), dim3(1024), 0, st, 0, d_part, chunks, inv_count, eps, d_stats); }, "gn_final");
   add_op(P, [=](cudaStream_t st) {
-    DISPATCH_T(dt, (gn_apply_kernel<T><<<dim3(chunks, N), threads, 0, st>>>(
+    DISPATCH_T(dt, (launch_k(gn_apply_kernel<T>, dim3(chunks, N), dim3(threads), 0, st, 0,
                        reinterpret_cast<const T*>(xp), ximg, ldx, reinterpret_cast<T*>(yp), yimg, ldy, C, HW, cg, pix,
                        d_stats, g, b, isilu)));
   }, "gn_apply", 0, 4.0 * N * HW * C);
@@ -802,7 +810,7 @@ Act Engine::layer_norm(Plan& P, const Act& x, const NormW& nw) {
   const float* g = nw.g;
   const float* b = nw.b;
   add_op(P, [=](cudaStream_t st) {
-    DISPATCH_T(dt, (layernorm_kernel<T><<<ceil_div(rows * 32, 256), 256, 0, st>>>(
+    DISPATCH_T(dt, (launch_k(layernorm_kernel<T>, dim3(ceil_div(rows * 32, 256)), dim3(256), 0, st, 0,
                        reinterpret_cast<const T*>(xp), ldx, reinterpret_cast<T*>(yp), ldy, static_cast<int>(rows), C, g, b,
                        1e-5f)));
   }, "layernorm", 0, 4.0 * rows * C);
@@ -817,7 +825,7 @@ Act Engine::upsample2x(Plan& P, const Act& x) {
   const int ldx = x.ld, ldy = y.ld, H = x.H, W = x.W, C = x.C, dt = dtype;
   const double N_ = x.N;
   add_op(P, [=](cudaStream_t st) {
-    DISPATCH_T(dt, (upsample2x_kernel<T><<<ceil_div(total, 256), 256, 0, st>>>(reinterpret_cast<const T*>(xp), ldx,
+    DISPATCH_T(dt, (launch_k(upsample2x_kernel<T>, dim3(ceil_div(total, 256)), dim3(256), 0, st, 0, reinterpret_cast<const T*>(xp), ldx,
                                                                              reinterpret_cast<T*>(yp), ldy, H, W, C, total)));
   }, "upsample2x", 0, 2.0 * 5.0 * N_ * H * W * C);
   return y;
@@ -830,7 +838,7 @@ void Engine::copy_channels(Plan& P, const Act& src, const Act& dst) {
   uint16_t* yp = dst.p;
   const int ldx = src.ld, ldy = dst.ld, C = src.C, dt = dtype;
   add_op(P, [=](cudaStream_t st) {
-    DISPATCH_T(dt, (copy2d_kernel<T><<<ceil_div(total, 256), 256, 0, st>>>(reinterpret_cast<const T*>(xp), ldx,
+    DISPATCH_T(dt, (launch_k(copy2d_kernel<T>, dim3(ceil_div(total, 256)), dim3(256), 0, st, 0, reinterpret_cast<const T*>(xp), ldx,
                                                                          reinterpret_cast<T*>(yp), ldy, C, total)));
   }, "concat_copy", 0, 4.0 * total * 8);
 }
@@ -931,12 +939,12 @@ Act Engine::attention(Plan& P, const Act& q, const Act& k, const Act& vt, int B,
     const int dt = dtype;
     if (Nk > 1024) {
       add_op(P, [=](cudaStream_t st) {
-        DISPATCH_T(dt, (softmax_kernel<T, 128><<<static_cast<unsigned>(rows), 128, 0, st>>>(S, lds, reinterpret_cast<T*>(Pm), lds,
+        DISPATCH_T(dt, (launch_k(softmax_kernel<T, 128>, dim3(static_cast<unsigned>(rows)), dim3(128), 0, st, 0, S, lds, reinterpret_cast<T*>(Pm), lds,
                                                                                           rows, Nk, lds)));
       }, "softmax", 0, 6.0 * rows * Nk);
     } else {
       add_op(P, [=](cudaStream_t st) {
-        DISPATCH_T(dt, (softmax_kernel<T, 32><<<static_cast<unsigned>((rows + 3) / 4), 128, 0, st>>>(
+        DISPATCH_T(dt, (launch_k(softmax_kernel<T, 32>, dim3(static_cast<unsigned>((rows + 3) / 4)), dim3(128), 0, st, 0,
                            S, lds, reinterpret_cast<T*>(Pm), lds, rows, Nk, lds)));
       }, "softmax", 0, 6.0 * rows * Nk);
     }
@@ -1015,7 +1023,7 @@ Act Engine::flash_attention(Plan& P, const Act& q, const Act& k, const Act& vt, 
   char shp[96];
   snprintf(shp, sizeof shp, "B=%d h=%d Nq=%d Nk=%d d=%d", B, heads, Nq, Nk, d);
   add_op(P, [=](cudaStream_t st) {
-    DISPATCH_T(dt, (flash_attn_kernel<T><<<grid, FA_THREADS, FA_SMEM, st>>>(tq, tk, tv, fp)));
+    DISPATCH_T(dt, (launch_k(flash_attn_kernel<T>, dim3(grid), dim3(FA_THREADS), FA_SMEM, st, 0, tq, tk, tv, fp)));
   }, "flash_attn", 4.0 * B * heads * Nq * Nk * d, 2.0 * (2.0 * B * Nq * C + 2.0 * kv_batch * Nk * C), shp);
   return out;
 }
@@ -1042,6 +1050,7 @@ void Engine::forward(const IO& io, int B, int H, int W, int direction, int text_
       if (P->graphs.size() >= 8) { cudaGraphExecDestroy(P->graphs.front().second); P->graphs.erase(P->graphs.begin()); }
       cudaGraph_t g = nullptr;
       I2IT_CUDA(cudaStreamBeginCapture(gstream_, cudaStreamCaptureModeThreadLocal));
+      g_pdl.enabled = use_pdl; g_pdl.prev_is_kernel = false;
       for (auto& op : P->ops) op(gstream_);
       I2IT_CUDA(cudaStreamEndCapture(gstream_, &g));
       I2IT_CUDA(cudaGraphInstantiate(&ge, g, 0));
@@ -1052,8 +1061,35 @@ void Engine::forward(const IO& io, int B, int H, int W, int direction, int text_
     I2IT_CUDA(cudaEventRecord(ev_out_, gstream_));
     I2IT_CUDA(cudaStreamWaitEvent(st, ev_out_, 0));
   } else {
+    g_pdl.enabled = use_pdl; g_pdl.prev_is_kernel = false;
     for (auto& op : P->ops) op(st);
     I2IT_CUDA(cudaGetLastError());
+  }
+  if (trace_on) dump_trace(*P, st);
+}
+
+// I2IT_TRACE=1: per GEMM launch, the median over CTAs of each phase stamp relative to the CTA's entry stamp (SM cycles).
+// slots: 1 prologue done | 2 first tile's loads issued | 3 all loads issued | 4 first operands landed | 5 first tile's MMAs
+// issued | 6 all MMAs issued | 7 first bias slice staged | 8 first accumulator ready | 9 first tile stored | 10 all tiles
+// stored | 11 CTA joined | 12 TMEM freed
+void Engine::dump_trace(Plan& P, cudaStream_t st) {
+  I2IT_CUDA(cudaStreamSynchronize(st));
+  I2IT_CUDA(cudaStreamSynchronize(gstream_));
+  int idx = 0;
+  for (auto& t : P.traces) {
+    std::vector<unsigned long long> h(static_cast<size_t>(t.grid) * 16);
+    I2IT_CUDA(cudaMemcpy(h.data(), t.buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    std::string line = "TRACE " + std::to_string(idx++) + " " + t.what + " |";
+    for (int sl = 1; sl <= 12; ++sl) {
+      std::vector<long long> d;
+      for (int c = 0; c < t.grid; ++c)
+        if (h[c * 16 + sl] && h[c * 16]) d.push_back(static_cast<long long>(h[c * 16 + sl] - h[c * 16]));
+      if (d.empty()) { line += " -"; continue; }
+      std::sort(d.begin(), d.end());
+      line += " " + std::to_string(d[d.size() / 2]);
+      if (sl == 12) line += " max " + std::to_string(d.back());
+    }
+    fprintf(stderr, "%s\n", line.c_str());
   }
 }
 
@@ -1067,6 +1103,7 @@ std::string Engine::profile_json(int reps, cudaStream_t st) {
   std::vector<double> ms(n, 0.0);
   for (int r = 0; r < reps; ++r) {
     I2IT_CUDA(cudaEventRecord(ev[0], st));
+    g_pdl.enabled = false;   // per-launch timing: full serialisation between kernels
     for (size_t i = 0; i < n; ++i) { P.ops[i](st); I2IT_CUDA(cudaEventRecord(ev[i + 1], st)); }
     I2IT_CUDA(cudaStreamSynchronize(st));
     for (size_t i = 0; i < n; ++i) { float t = 0; I2IT_CUDA(cudaEventElapsedTime(&t, ev[i], ev[i + 1])); ms[i] += t / reps; }

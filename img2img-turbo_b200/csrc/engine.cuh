@@ -56,6 +56,32 @@ struct PW {                        // prepared (folded, re-laid-out) weight: [ta
   float* bias = nullptr;
   int rows = 0, cin = 0, cin_pad = 0, taps = 1;
 };
+// ---- kernel launch for plan ops: programmatic dependent launch (see pdl_sync in common.cuh) when the previous op of the
+// plan was also a kernel; `cluster` > 0 adds a (cluster,1,1) cluster dimension.  Executor state, one engine call per thread.
+struct PdlState { bool enabled = true; bool prev_is_kernel = false; };
+extern thread_local PdlState g_pdl;
+template <typename... KA, typename... A>
+inline void launch_k(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, A&&... args) {
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  unsigned n = 0;
+  if (cluster > 0) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = cluster; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (g_pdl.enabled && g_pdl.prev_is_kernel) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = at; cfg.numAttrs = n;
+  cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);
+  g_pdl.prev_is_kernel = true;
+}
+
 struct NormW { const float* g = nullptr; const float* b = nullptr; int C = 0; };
 
 struct IO {
@@ -75,6 +101,8 @@ struct Plan {
   std::vector<std::function<void(cudaStream_t)>> ops;  // one kernel launch each
   std::vector<OpMeta> meta;                            // parallel to ops
   std::map<std::string, Act> stages;
+  struct Trace { unsigned long long* buf; int grid; std::string what; };
+  std::vector<Trace> traces;                           // I2IT_TRACE=1 only
   std::vector<std::shared_ptr<void>> keep;
   IO io;
   std::vector<std::pair<IO, cudaGraphExec_t>> graphs;  // small cache: one instantiated graph per distinct IO pointer set
@@ -170,9 +198,10 @@ class Engine {
   void launch_gemm(Plan& P, const TmapSpec& sa, TmapSpec sb, const TapGemmParams& p, bool out_from_io, const char* kind,
                    double k_valid, double bytes, const TmapSpec* sa2 = nullptr, const TmapSpec* sb2 = nullptr,
                    const TmapSpec* shalo = nullptr);
-  bool use_pair = true, use_halo = true, use_idres = true;
+  bool use_pair = true, use_halo = true, use_idres = true, use_pdl = false, trace_on = false, use_ostage = true;
   long long pair_min_tiles = 296;   // CTA-pair kernel from two waves of tiles upwards (tunable: I2IT_PAIR_MIN_TILES)
   std::string profile_json(int reps, cudaStream_t st);
+  void dump_trace(Plan& P, cudaStream_t st);
   int pick_bn(long long m_tiles, int N, bool even32) const;
 
   int* d_err = nullptr;      // device alias of a mapped host word written by the tapgemm watchdog

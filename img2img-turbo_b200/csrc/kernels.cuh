@@ -15,6 +15,7 @@ namespace i2it {
 template <typename T>
 __global__ void gn_stats_kernel(const T* __restrict__ x, long long img_stride, int ld, int C, int HW, int cg,
                                 int pix_per_cta, float* __restrict__ partial /*[N][chunks][32][2]*/) {
+  pdl_sync();
   extern __shared__ float s_acc[];   // [rows][2][C]: per-row partials, reduced in a fixed order (bit-reproducible)
   const int vecs = C >> 3;
   const int vx = threadIdx.x % vecs, vy = threadIdx.x / vecs, rows = blockDim.x / vecs;
@@ -60,19 +61,33 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, long long img_stride, i
 
 static __global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, double inv_count, float eps,
                                           float* __restrict__ stats /*[N][32][2] = mean, rstd*/) {
-  // block = 1024 threads: warp g reduces group g over the chunks (fixed lane-strided order + butterfly: reproducible)
-  const int n = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_sync();
+  // block = 1024 threads = 32 chunk-lanes x 32 groups.  Thread (cl, g) sums chunks cl, cl+32, ... of group g with
+  // independent coalesced float2 loads (a warp reads the 256 B of one chunk row), then the 32 chunk-lanes of a group are
+  // combined in a fixed order through shared memory: reproducible, no atomics, and no dependent-load chain.
+  __shared__ double2 red[32][33];
+  const int n = blockIdx.x, g = threadIdx.x & 31, cl = threadIdx.x >> 5;
+  const float2* base = reinterpret_cast<const float2*>(partial) + static_cast<long long>(n) * chunks * 32 + g;
   double a = 0.0, b = 0.0;
-  for (int c = lane; c < chunks; c += 32) {
-    const float* o = partial + ((static_cast<long long>(n) * chunks + c) * 32 + g) * 2;
-    a += o[0]; b += o[1];
+  int c = cl;
+  for (; c + 96 < chunks; c += 128) {
+    const float2 v0 = base[static_cast<long long>(c) * 32], v1 = base[static_cast<long long>(c + 32) * 32];
+    const float2 v2 = base[static_cast<long long>(c + 64) * 32], v3 = base[static_cast<long long>(c + 96) * 32];
+    a += static_cast<double>(v0.x); b += static_cast<double>(v0.y);
+    a += static_cast<double>(v1.x); b += static_cast<double>(v1.y);
+    a += static_cast<double>(v2.x); b += static_cast<double>(v2.y);
+    a += static_cast<double>(v3.x); b += static_cast<double>(v3.y);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, o);
-    b += __shfl_xor_sync(0xffffffffu, b, o);
+  for (; c < chunks; c += 32) {
+    const float2 v = base[static_cast<long long>(c) * 32];
+    a += static_cast<double>(v.x); b += static_cast<double>(v.y);
   }
-  if (lane == 0) {
+  red[cl][g] = make_double2(a, b);
+  __syncthreads();
+  if (cl == 0) {
+    a = 0.0; b = 0.0;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) { a += red[i][g].x; b += red[i][g].y; }
     const double mean = a * inv_count;
     double var = b * inv_count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -85,6 +100,7 @@ template <typename T>
 __global__ void gn_apply_kernel(const T* __restrict__ x, long long ximg, int ldx, T* __restrict__ y, long long yimg,
                                 int ldy, int C, int HW, int cg, int pix_per_cta, const float* __restrict__ stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int silu) {
+  pdl_sync();
   const int vecs = C >> 3;
   const int vx = threadIdx.x % vecs, vy = threadIdx.x / vecs, rows = blockDim.x / vecs;
   const int n = blockIdx.y;
@@ -132,6 +148,7 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, long long ximg, int ldx
 template <typename T>
 __global__ void layernorm_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int rows, int C,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+  pdl_sync();
   constexpr int MAXV = 5;   // C <= 1280
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -169,11 +186,14 @@ __global__ void layernorm_kernel(const T* __restrict__ x, int ldx, T* __restrict
     const int vi = lane + 32 * k;
     if (vi < vecs) {
       uint32_t o[4];
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + vi * 8), g1 = *reinterpret_cast<const float4*>(gamma + vi * 8 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(beta + vi * 8), b1 = *reinterpret_cast<const float4*>(beta + vi * 8 + 4);
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int c = vi * 8 + 2 * i;
-        o[i] = Elem<T>::pack((v[k][2 * i] - mean) * rstd * gamma[c] + beta[c],
-                             (v[k][2 * i + 1] - mean) * rstd * gamma[c + 1] + beta[c + 1]);
+        o[i] = Elem<T>::pack((v[k][2 * i] - mean) * rstd * gm[2 * i] + bt[2 * i],
+                             (v[k][2 * i + 1] - mean) * rstd * gm[2 * i + 1] + bt[2 * i + 1]);
       }
       st16(yr + vi * 8, make_uint4(o[0], o[1], o[2], o[3]));
     }
@@ -187,6 +207,7 @@ __global__ void layernorm_kernel(const T* __restrict__ x, int ldx, T* __restrict
 template <typename T, int TPR>
 __global__ void softmax_kernel(const float* __restrict__ s, long long lds, T* __restrict__ pr, long long ldp,
                                long long rows, int nk, int nk_pad) {
+  pdl_sync();
   constexpr int RPB = 128 / TPR;
   const long long row = static_cast<long long>(blockIdx.x) * RPB + threadIdx.x / TPR;
   const int tr = threadIdx.x % TPR;
@@ -237,6 +258,7 @@ __global__ void softmax_kernel(const float* __restrict__ s, long long lds, T* __
 // NCHW [B,3,H,W] (act dtype) -> NHWC8 (channels 3..7 zero): the 3-channel boundary of vae.encode.
 template <typename T>
 __global__ void pack_input_kernel(const T* __restrict__ x, T* __restrict__ y, int C, long long HW, long long total) {
+  pdl_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // over B*HW pixels
   if (i >= total) return;
   const long long n = i / HW, p = i % HW;
@@ -253,6 +275,7 @@ __global__ void pack_input_kernel(const T* __restrict__ x, T* __restrict__ y, in
 // Turns encoder.conv_in (Cin=3: 16-byte TMA rows x 9 taps, TMA-request bound) into ONE K=32 GEMM tap with 64-byte rows.
 template <typename T>
 __global__ void pack_input_im2col_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, long long total) {
+  pdl_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // over B*H*W pixels
   if (i >= total) return;
   const long long HW = static_cast<long long>(H) * W;
@@ -283,6 +306,7 @@ template <typename T>
 __global__ void latent_sample_kernel(const T* __restrict__ mom, int ldm, const T* __restrict__ eps_nchw,
                                      const T* __restrict__ noise_nchw, float r, float sf, T* __restrict__ z,
                                      long long HW, long long total) {
+  pdl_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const long long n = i / HW, p = i % HW;
@@ -310,6 +334,7 @@ template <typename T>
 __global__ void ddpm_step_kernel(const T* __restrict__ zin /*NHWC8*/, const T* __restrict__ pred, int ldp,
                                  float s1, float sa, float inv_sf, T* __restrict__ dec_in /*NHWC8*/,
                                  T* __restrict__ x0_nchw /*nullable*/, long long HW, long long total) {
+  pdl_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const long long n = i / HW, p = i % HW;
@@ -328,6 +353,7 @@ __global__ void ddpm_step_kernel(const T* __restrict__ zin /*NHWC8*/, const T* _
 template <typename T>
 __global__ void upsample2x_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int H, int W, int C,
                                   long long total /* B*2H*2W*(C/8) */) {
+  pdl_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int vecs = C >> 3;
@@ -343,6 +369,7 @@ __global__ void upsample2x_kernel(const T* __restrict__ x, int ldx, T* __restric
 // strided 2-D copy of 16-byte vectors: rows x (C/8) vectors (torch.cat along channels)
 template <typename T>
 __global__ void copy2d_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int C, long long total) {
+  pdl_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int vecs = C >> 3;

@@ -61,7 +61,7 @@ Act Engine::build_vae_encoder(Plan& P, const std::string& vp, int B, int H, int 
     Plan* plan = &P;
     const int dt = dtype, hh = H, ww = W;
     add_op(P, [=](cudaStream_t st) {
-      DISPATCH_T(dt, (pack_input_im2col_kernel<T><<<ceil_div_i(total, 128), 128, 0, st>>>(
+      DISPATCH_T(dt, (launch_k(pack_input_im2col_kernel<T>, dim3(ceil_div_i(total, 128)), dim3(128), 0, st, 0,
                          reinterpret_cast<const T*>(plan->io.x), reinterpret_cast<T*>(yp), hh, ww, total)));
     }, "pack_im2col", 0, 2.0 * total * (3 + 32));
   }
@@ -97,7 +97,7 @@ Act Engine::build_vae_encoder(Plan& P, const std::string& vp, int B, int H, int 
     const float sf = cfg.scaling_factor;
     P.keep.push_back(mom.hold);
     add_op(P, [=](cudaStream_t st) {
-      DISPATCH_T(dt, (latent_sample_kernel<T><<<ceil_div_i(total, 128), 128, 0, st>>>(
+      DISPATCH_T(dt, (launch_k(latent_sample_kernel<T>, dim3(ceil_div_i(total, 128)), dim3(128), 0, st, 0,
                          reinterpret_cast<const T*>(mp), ldm, reinterpret_cast<const T*>(plan->io.eps),
                          reinterpret_cast<const T*>(plan->io.noise), plan->io.r, sf, reinterpret_cast<T*>(zp), HW, total)));
     });
@@ -198,7 +198,10 @@ Act Engine::build_unet(Plan& P, const Act& z, int text_batch) {
     uint16_t* tp = text_.p;
     const size_t bytes = static_cast<size_t>(text_batch) * 77 * cfg.cross_dim * 2;
     Plan* plan = &P;
-    add_op(P, [=](cudaStream_t st) { cudaMemcpyAsync(tp, plan->io.text, bytes, cudaMemcpyDeviceToDevice, st); });
+    add_op(P, [=](cudaStream_t st) {
+      cudaMemcpyAsync(tp, plan->io.text, bytes, cudaMemcpyDeviceToDevice, st);
+      g_pdl.prev_is_kernel = false;   // a copy node: the next kernel takes a full dependency
+    });
   }
   Act s;
   if (has(u + ".conv_in.conv_in_pretrained.weight")) {
@@ -277,7 +280,7 @@ Plan* Engine::plan_for(int B, int H, int W, int direction, int text_batch) {
     P.keep.push_back(z.hold);
     P.keep.push_back(pred.hold);
     add_op(P, [=](cudaStream_t st) {
-      DISPATCH_T(dt, (ddpm_step_kernel<T><<<ceil_div_i(total, 128), 128, 0, st>>>(
+      DISPATCH_T(dt, (launch_k(ddpm_step_kernel<T>, dim3(ceil_div_i(total, 128)), dim3(128), 0, st, 0,
                          reinterpret_cast<const T*>(zp), reinterpret_cast<const T*>(pp), ldp, s1, sa, inv_sf,
                          reinterpret_cast<T*>(dp), reinterpret_cast<T*>(plan->io.out_latent), HW, total)));
     });

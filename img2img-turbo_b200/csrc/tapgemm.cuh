@@ -31,7 +31,12 @@ constexpr int TG_A_STAGE = TG_BM * TG_BK * 2;    // 16 KiB
 constexpr int TG_B_STAGE = 256 * TG_BK * 2;      // 32 KiB (BN <= 256)
 constexpr int TG_BAR_BYTES = 256;
 constexpr int TG_BIAS_BYTES = 2 * 256 * 4;       // per-tile bias slice, double-buffered like the accumulators
-constexpr int TG_SMEM = TG_STAGES * (TG_A_STAGE + TG_B_STAGE) + TG_BAR_BYTES + TG_BIAS_BYTES + 1024;  // +1024: manual alignment
+// epilogue store staging: each epilogue warp owns a 32-row x 64-byte tile (XOR-swizzled 16-byte chunks).  A thread holds one
+// accumulator ROW, so direct stores touch 32 different lines per instruction (measured: ~6000 cycles per 128x160 tile, the
+// limiter of every small-K GEMM); through the tile a store instruction writes 8 rows x 64 contiguous bytes instead.
+constexpr int TG_OSTG_WARP = 32 * 64;
+constexpr int TG_OSTG_BYTES = 8 * TG_OSTG_WARP;
+constexpr int TG_SMEM = TG_STAGES * (TG_A_STAGE + TG_B_STAGE) + TG_BAR_BYTES + TG_BIAS_BYTES + TG_OSTG_BYTES + 1024;  // +1024: manual alignment
 constexpr int TG_EPI_WARPS = 8;        // two warps per TMEM lane quarter: they alternate 32-column rounds
 constexpr int TG_THREADS = (TG_EPI_WARPS + 2) * 32;   // + TMA producer warp + MMA issuer warp
 constexpr int TG_ACC_COLS = 256;       // TMEM columns per accumulator stage
@@ -70,6 +75,8 @@ struct TapGemmParams {
   float alpha;
   int act;
   int* err;               // device error word (watchdog)
+  int ostage;             // 1: stage 16-bit row-major output rounds through smem for coalesced stores (I2IT_NO_OSTG=1 -> 0)
+  unsigned long long* trace;   // optional (I2IT_TRACE=1): 16 %clock64 stamps per CTA at the phase boundaries, else nullptr
 };
 
 // ------------------------------------------------------------------------------------------
@@ -170,6 +177,23 @@ inline uint32_t make_idesc(int dtype, int bn) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(bn >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+__device__ __forceinline__ void sts16(uint32_t saddr, const uint4& u) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds16(uint32_t saddr) {
+  uint4 u;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(saddr) : "memory");
+  return u;
+}
+
+// timeline stamp for the diagnostic trace (build with `make TRACE=1`, run with I2IT_TRACE=1; one thread per role writes;
+// cycles are per-SM, compare within a CTA only)
+__device__ __forceinline__ void tg_stamp(const TapGemmParams& p, int slot) {
+#ifdef I2IT_TRACE_BUILD   // `make TRACE=1`: even a never-taken stamp in the issue loops costs ~2 % of a step, so it is compiled out by default
+  if (p.trace) p.trace[blockIdx.x * 16 + slot] = static_cast<unsigned long long>(clock64());
+#endif
+}
+
 struct TileCoord {
   int nt, t[4];
 };
@@ -188,7 +212,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int til
 template <typename T>
 __device__ __forceinline__ void epilogue_chunk(const TapGemmParams& p, const uint32_t (&raw)[16], int col0, long long obase,
                                                long long rbase, float rbias, const float* sbias, bool rfast, const uint4& r0,
-                                               const uint4& r1) {
+                                               const uint4& r1, uint32_t stg = 0u, int stg_chunk = 0, int stg_row = 0) {
   float v[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
@@ -211,7 +235,12 @@ __device__ __forceinline__ void epilogue_chunk(const TapGemmParams& p, const uin
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] += Elem<T>::to_f(rptr[i]);
     }
-    if (full && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0)) {
+    if (stg) {                                    // staged round (caller checked: full columns, aligned rows)
+      uint4 u;
+      u.x = Elem<T>::pack(o[0], o[1]); u.y = Elem<T>::pack(o[2], o[3]);
+      u.z = Elem<T>::pack(o[4], o[5]); u.w = Elem<T>::pack(o[6], o[7]);
+      sts16(stg + ((stg_chunk ^ (stg_row >> 1)) & 3) * 16, u);
+    } else if (full && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0)) {
       uint4 u;
       u.x = Elem<T>::pack(o[0], o[1]); u.y = Elem<T>::pack(o[2], o[3]);
       u.z = Elem<T>::pack(o[4], o[5]); u.w = Elem<T>::pack(o[6], o[7]);
@@ -252,7 +281,15 @@ __device__ __forceinline__ void epilogue_chunk(const TapGemmParams& p, const uin
     }
   } else {
     T* optr = reinterpret_cast<T*>(p.out) + obase + col0 * p.ocol;
-    if (full && p.ocol == 1 && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0)) {
+    if (stg) {
+      uint4 u0, u1;
+      u0.x = Elem<T>::pack(v[0], v[1]);   u0.y = Elem<T>::pack(v[2], v[3]);
+      u0.z = Elem<T>::pack(v[4], v[5]);   u0.w = Elem<T>::pack(v[6], v[7]);
+      u1.x = Elem<T>::pack(v[8], v[9]);   u1.y = Elem<T>::pack(v[10], v[11]);
+      u1.z = Elem<T>::pack(v[12], v[13]); u1.w = Elem<T>::pack(v[14], v[15]);
+      sts16(stg + (((2 * stg_chunk) ^ (stg_row >> 1)) & 3) * 16, u0);
+      sts16(stg + (((2 * stg_chunk + 1) ^ (stg_row >> 1)) & 3) * 16, u1);
+    } else if (full && p.ocol == 1 && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0)) {
       uint4 u0, u1;
       u0.x = Elem<T>::pack(v[0], v[1]);   u0.y = Elem<T>::pack(v[2], v[3]);
       u0.z = Elem<T>::pack(v[4], v[5]);   u0.w = Elem<T>::pack(v[6], v[7]);
@@ -273,7 +310,10 @@ __device__ __forceinline__ void epilogue_chunk(const TapGemmParams& p, const uin
 template <typename T>
 __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const TileCoord& c, int row, int warp, int j1, int j2,
                                               int j3, int j4, int acc, int aphase, uint32_t tmem_base, float* s_bias,
-                                              uint32_t tfull_bar_addr) {
+                                              uint32_t tfull_bar_addr, bool stamp = false) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t ostg_warp = smem_u32(s_bias) + TG_BIAS_BYTES + warp * TG_OSTG_WARP;   // this warp's staging tile
+  const uint32_t ostg_row = ostg_warp + lane * 64;
   const int grp = warp >> 2;                     // which of the two warps sharing this TMEM lane quarter
   const int g1 = c.t[0] * p.box[0] + j1, g2 = c.t[1] * p.box[1] + j2, g3 = c.t[2] * p.box[2] + j3,
             g4 = c.t[3] * p.box[3] + j4;
@@ -290,6 +330,7 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const Tile
       sb[cc] = (n0 + cc < p.N) ? p.bias[n0 + cc] : 0.f;
   }
   asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps only
+  if (stamp) tg_stamp(p, 7);
 
   // Residual reads do not depend on the accumulator: this thread's WHOLE residual slice (its row x the 32-column rounds
   // r = grp, grp+2, ...; <= 256 B) is requested before the accumulator wait, so global-load latency overlaps the mainloop
@@ -316,6 +357,7 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const Tile
 
   mbar_wait(tfull_bar_addr, aphase, p.err, 4);
   tc_fence_after();
+  if (stamp) tg_stamp(p, 8);
   const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + acc * TG_ACC_COLS;
 
 #pragma unroll
@@ -329,11 +371,33 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const Tile
     tc_ld16(taddr + c0, raw0);
     if (nch == 2) tc_ld16(taddr + c0 + 16, raw1);
     tc_wait_ld();
-    if (!row_ok) continue;
     const int col0 = n0 + c0;
-    if (col0 < p.N) epilogue_chunk<T>(p, raw0, col0, obase, rbase, rbias, sb + c0, fast[i], rq[i][0], rq[i][1]);
-    if (nch == 2 && col0 + 16 < p.N)
-      epilogue_chunk<T>(p, raw1, col0 + 16, obase, rbase, rbias, sb + c0 + 16, fast[i], rq[i][2], rq[i][3]);
+    // Staged round (warp-uniform decision): 16-bit contiguous output, every column of the round inside N, every row 16-byte
+    // aligned.  Otherwise (fp32 / NCHW / ragged last tile) each thread stores its own row directly as before.
+    const bool geglu = p.act == TG_ACT_GEGLU;
+    const long long ocol0 = geglu ? (col0 >> 1) : col0;
+    const bool aligned = !row_ok || (((reinterpret_cast<uintptr_t>(p.out) + 2 * (obase + ocol0)) & 15) == 0);
+    const bool staged = p.ostage && !p.out_fp32 && p.ocol == 1 && (col0 + 16 * nch <= p.N) && __all_sync(0xffffffffu, aligned);
+    const uint32_t stg = staged ? ostg_row : 0u;
+    if (row_ok) {
+      if (col0 < p.N) epilogue_chunk<T>(p, raw0, col0, obase, rbase, rbias, sb + c0, fast[i], rq[i][0], rq[i][1], stg, 0, lane);
+      if (nch == 2 && col0 + 16 < p.N)
+        epilogue_chunk<T>(p, raw1, col0 + 16, obase, rbase, rbias, sb + c0 + 16, fast[i], rq[i][2], rq[i][3], stg, 1, lane);
+    }
+    if (staged) {
+      // 16-byte chunks per row in this round: 4 (32 columns), 2 (16 columns, or 32 GEGLU columns), 1 (16 GEGLU columns)
+      const int ch16 = geglu ? nch : 2 * nch;
+      const int sh = (ch16 == 4) ? 2 : (ch16 == 2 ? 1 : 0);
+      __syncwarp();
+      for (int it = 0; it < ch16; ++it) {
+        const int rr = (it << (5 - sh)) + (lane >> sh), ch = lane & (ch16 - 1);
+        const long long ob = __shfl_sync(0xffffffffu, obase, rr);
+        const int ok = __shfl_sync(0xffffffffu, static_cast<int>(row_ok), rr);
+        const uint4 u = lds16(ostg_warp + rr * 64 + ((ch ^ (rr >> 1)) & 3) * 16);
+        if (ok) st16(reinterpret_cast<T*>(p.out) + ob + ocol0 + ch * 8, u);
+      }
+      __syncwarp();                              // the tile is rewritten by the next round
+    }
   }
 }
 
@@ -357,6 +421,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* const s_bias = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + TG_BAR_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) tg_stamp(p, 0);
   const int total_tiles = p.n_tiles * p.tdim[0] * p.tdim[1] * p.tdim[2] * p.tdim[3];
   int steps = 0;
   for (int t = 0; t < p.num_taps; ++t) steps += p.tap_kc[t];
@@ -377,6 +442,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_sync();   // prologue (barriers, TMEM, descriptor prefetch) overlaps the previous kernel's tail; no global access before here
+  if (threadIdx.x == 0) tg_stamp(p, 1);
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
@@ -408,7 +475,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int t = 0; t < p.nprim; ++t) load_step(t, kc);
       for (int t = p.nprim; t < p.num_taps; ++t)
         for (int kc = 0; kc < p.tap_kc[t]; ++kc) load_step(t, kc);
+      if (tile == static_cast<int>(blockIdx.x) && lane == 0) tg_stamp(p, 2);   // first tile's loads all issued
     }
+    if (lane == 0) tg_stamp(p, 3);
   } else if (warp == TG_EPI_WARPS + 1) {
     // ================================ MMA issuer (warp-uniform loop, elected lane issues) ================================
     int stage = 0, phase = 0, iter = 0;
@@ -420,6 +489,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int s = 0; s < steps; ++s) {
         mbar_wait(full_bar(stage), phase, p.err, 3);
         tc_fence_after();
+        if (iter == 0 && s == 0 && lane == 0) tg_stamp(p, 4);                   // first operands landed
         if (elect_one()) {
           const uint64_t adesc = umma_desc_sw128(sA + stage * TG_A_STAGE);
           const uint64_t bdesc = umma_desc_sw128(sB + stage * BST);
@@ -432,7 +502,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (++stage == NS) { stage = 0; phase ^= 1; }
       }
+      if (iter == 0 && lane == 0) tg_stamp(p, 5);                               // first tile fully issued
     }
+    if (lane == 0) tg_stamp(p, 6);
   } else {
     // ================================ epilogue (warps 0..7) ================================
     const int row = (warp & 3) * 32 + lane;
@@ -445,17 +517,22 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       const int acc = iter & 1, aphase = (iter >> 1) & 1;
       const TileCoord c = decode_tile(p, tile);
-      epilogue_tile<T>(p, c, row, warp, j1, j2, j3, j4, acc, aphase, tmem_base, s_bias, tfull_bar(acc));
+      epilogue_tile<T>(p, c, row, warp, j1, j2, j3, j4, acc, aphase, tmem_base, s_bias, tfull_bar(acc),
+                       iter == 0 && threadIdx.x == 0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (iter == 0 && threadIdx.x == 0) tg_stamp(p, 9);                        // first tile stored
     }
+    if (threadIdx.x == 0) tg_stamp(p, 10);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) tg_stamp(p, 11);
   if (warp == TG_EPI_WARPS + 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (lane == 0) tg_stamp(p, 12);
   }
 }
 

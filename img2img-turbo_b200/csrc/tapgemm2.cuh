@@ -25,7 +25,7 @@ constexpr int TG2_HALO_STAGES = 3;
 constexpr int TG2_DATA_BYTES = (TG2_STAGES * (TG_A_STAGE + TG2_B_STAGE) > TG2_HALO_STAGES * TG2_HALO_BYTES + TG2_STAGES * TG2_B_STAGE)
                                    ? TG2_STAGES * (TG_A_STAGE + TG2_B_STAGE)
                                    : TG2_HALO_STAGES * TG2_HALO_BYTES + TG2_STAGES * TG2_B_STAGE;
-constexpr int TG2_SMEM = TG2_DATA_BYTES + TG_BAR_BYTES + TG_BIAS_BYTES + 1024;
+constexpr int TG2_SMEM = TG2_DATA_BYTES + TG_BAR_BYTES + TG_BIAS_BYTES + TG_OSTG_BYTES + 1024;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -110,6 +110,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   float* const s_bias = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + TG_BAR_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) tg_stamp(p, 0);
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int m_tiles = p.tdim[0] * p.tdim[1] * p.tdim[2] * p.tdim[3];
@@ -150,6 +151,8 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_sync();   // prologue (barriers, TMEM, descriptor prefetch) overlaps the previous kernel's tail; no global access before here
+  if (threadIdx.x == 0) tg_stamp(p, 1);
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
@@ -207,7 +210,9 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int t = p.nprim; t < p.num_taps; ++t)
           for (int kc = 0; kc < p.tap_kc[t]; ++kc) load_step(t, kc);
       }
+      if (pt == cluster_id && lane == 0) tg_stamp(p, 2);   // first tile's loads all issued
     }
+    if (lane == 0) tg_stamp(p, 3);
   } else if (warp == TG_EPI_WARPS + 1) {
     // ================================ MMA issuer (leader CTA only) ================================
     if (leader) {
@@ -245,6 +250,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int s = 0; s < steps; ++s) {
             mbar_wait(full_bar(stage), phase, p.err, 23);
             tc_fence_after();
+            if (iter == 0 && s == 0 && lane == 0) tg_stamp(p, 4);               // first operands landed (both CTAs)
             if (elect_one()) {
               const uint64_t adesc = umma_desc_sw128(sA + stage * TG_A_STAGE);
               const uint64_t bdesc = umma_desc_sw128(sB + stage * BST);
@@ -258,7 +264,9 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (++stage == NS) { stage = 0; phase ^= 1; }
           }
         }
+        if (iter == 0 && lane == 0) tg_stamp(p, 5);                             // first tile fully issued
       }
+      if (lane == 0) tg_stamp(p, 6);
     }
   } else {
     // ================================ epilogue (both CTAs, own 128 rows) ================================
@@ -272,18 +280,23 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++iter) {
       const int acc = iter & 1, aphase = (iter >> 1) & 1;
       const TileCoord c = decode_pair(pt);
-      epilogue_tile<T>(p, c, row, warp, j1, j2, j3, j4, acc, aphase, tmem_base, s_bias, tfull_bar(acc));
+      epilogue_tile<T>(p, c, row, warp, j1, j2, j3, j4, acc, aphase, tmem_base, s_bias, tfull_bar(acc),
+                       iter == 0 && threadIdx.x == 0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
+      if (iter == 0 && threadIdx.x == 0) tg_stamp(p, 9);                        // first tile stored
     }
+    if (threadIdx.x == 0) tg_stamp(p, 10);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) tg_stamp(p, 11);
   cluster_sync_all();                                   // nobody leaves (or frees TMEM) while the peer may still signal it
   if (warp == TG_EPI_WARPS + 1) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (lane == 0) tg_stamp(p, 12);
   }
 }
 
