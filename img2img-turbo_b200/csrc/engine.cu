@@ -123,7 +123,7 @@ Engine::Engine(const i2it_config& c) : cfg(c), dtype(c.dtype) {
   use_ostage = std::getenv("I2IT_NO_OSTG") == nullptr;
   pair_min_tiles = std::getenv("I2IT_PAIR_MIN_TILES") ? atoll(std::getenv("I2IT_PAIR_MIN_TILES")) : 2ll * num_sms;
   use_idres = std::getenv("I2IT_NO_IDRES") == nullptr;
-  use_halo = std::getenv("I2IT_HALO") != nullptr;     // experimental (r01: descriptor semantics of shifted swizzled views unresolved -> wrong results); off by default
+  use_halo = std::getenv("I2IT_NO_HALO") == nullptr;   // 3x3 convs: one halo tile per k-chunk instead of nine shifted A boxes
   I2IT_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG2_SMEM));
   I2IT_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG2_SMEM));
   int* h = nullptr;

@@ -70,12 +70,13 @@ __device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
 }
 
 // descriptor of a tap's view into the halo tile: rows of 128 B, 8-row groups 2048 B apart (one image row of the 16-pixel
-// pitch), swizzle phase of the first row = dx (start is dx rows past a 1024-byte boundary)
-__device__ __forceinline__ uint64_t umma_desc_halo(uint32_t saddr, uint32_t dx) {
+// pitch).  The start address is dx rows past a 1024-byte swizzle-atom boundary; the tensor core derives the 128B-swizzle phase
+// from the absolute shared-memory address bits (the same bits TMA used when it wrote the tile), so base_offset stays 0
+// (measured: base_offset = dx reads the wrong chunks, 0 is bit-exact against the nine-box path).
+__device__ __forceinline__ uint64_t umma_desc_halo(uint32_t saddr) {
   uint64_t d = static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>(2048 >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(dx & 7) << 49;      // base_offset
   d |= static_cast<uint64_t>(2) << 61;           // SWIZZLE_128B
   return d;
 }
@@ -232,7 +233,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               if (elect_one()) {
                 // tap (dy,dx) = rows shifted by dy image rows (2048 B) and dx pixels (128 B) inside the halo tile
                 const uint32_t dy = static_cast<uint32_t>(p.tap_a[t][2] + 1), dx = static_cast<uint32_t>(p.tap_a[t][1] + 1);
-                const uint64_t adesc = umma_desc_halo(sA + hs * TG2_HALO_BYTES + dy * 2048u + dx * 128u, dx);
+                const uint64_t adesc = umma_desc_halo(sA + hs * TG2_HALO_BYTES + dy * 2048u + dx * 128u);
                 const uint64_t bdesc = umma_desc_sw128(sB + stage * BST);
 #pragma unroll
                 for (int k = 0; k < TG_BK / 16; ++k)
