@@ -131,6 +131,61 @@ def test_cyclegan_host_behaviour():
     assert any(k.startswith("vae_b2a.") for k in m._sd)
 
 
+def test_cyclegan_checkpoint_format(tmp_path):
+    """The .pkl written by train_cyclegan_turbo.py:293-307 (read at cyclegan_turbo.py:162-190): three UNet adapter dicts with
+    adapter-less peft keys, two VAE dicts whose keys carry the vae./vae_b2a. prefix, peft 'base_layer.' variants."""
+    import weights as W
+    from cyclegan_turbo import CycleGAN_Turbo
+    m = CycleGAN_Turbo(cfg=W.TINY, text_stack=_text_stack(), synthetic_caption="c", synthetic_direction="a2b")
+    enc_key = next(k for k in m._sd if k.startswith("unet.") and ".lora_B.default_encoder." in k)
+    dec_key = next(k for k in m._sd if k.startswith("unet.") and ".lora_B.default_decoder." in k)
+    oth_key = next(k for k in m._sd if k.startswith("unet.") and ".lora_B.default_others." in k)
+    strip = lambda k, a: k[len("unet."):].replace(f".lora_B.{a}.", ".lora_B.")
+    skip_key = next(k for k in m._sd if k.startswith("vae.") and "skip_conv_1" in k)
+    conv_key = next(k for k in m._sd if k.startswith("vae_b2a.") and k.endswith("conv_in.weight"))
+    ck = {"rank_unet": 8, "rank_vae": 4,
+          "sd_encoder": {strip(enc_key, "default_encoder"): torch.full_like(m._sd[enc_key], 1.5)},
+          "sd_decoder": {strip(dec_key, "default_decoder"): torch.full_like(m._sd[dec_key], 2.5)},
+          "sd_other": {strip(oth_key, "default_others"): torch.full_like(m._sd[oth_key], 3.5)},
+          "sd_vae_enc": {conv_key.replace("conv_in.weight", "conv_in.base_layer.weight"): torch.full_like(m._sd[conv_key], 4.5)},
+          "sd_vae_dec": {skip_key: torch.full_like(m._sd[skip_key], 5.5)}}
+    p = str(tmp_path / "cyc.pkl")
+    torch.save(ck, p)
+    with pytest.warns(UserWarning):                    # no SD-Turbo base offline: checkpoint tensors over a seeded base
+        m2 = CycleGAN_Turbo(pretrained_path=p, cfg=W.TINY, text_stack=_text_stack())
+    for k, v in ((enc_key, 1.5), (dec_key, 2.5), (oth_key, 3.5), (conv_key, 4.5), (skip_key, 5.5)):
+        assert torch.all(m2._sd[k] == v), k
+    with pytest.raises(ValueError):
+        CycleGAN_Turbo(pretrained_name="no_such_model", cfg=W.TINY, text_stack=_text_stack())
+
+
+def test_sd_turbo_snapshot_overlay(tmp_path, monkeypatch):
+    """Real base weights come from a local snapshot ($I2IT_SD_TURBO_DIR/{unet,vae}/diffusion_pytorch_model.safetensors);
+    pre-0.14 VAE attention key names (query/key/value/proj_attn) are mapped to to_q/to_k/to_v/to_out.0."""
+    from safetensors.torch import save_file
+    import _host
+    (tmp_path / "unet").mkdir()
+    (tmp_path / "vae").mkdir()
+    save_file({"conv_in.weight": torch.full((2, 2), 7.0, dtype=torch.float16)},
+              str(tmp_path / "unet" / "diffusion_pytorch_model.safetensors"))
+    save_file({"encoder.mid_block.attentions.0.query.weight": torch.full((2, 2), 1.0),
+               "encoder.mid_block.attentions.0.proj_attn.bias": torch.full((2,), 2.0),
+               "decoder.conv_out.bias": torch.full((3,), 3.0)},
+              str(tmp_path / "vae" / "diffusion_pytorch_model.safetensors"))
+    sd = {}
+    monkeypatch.delenv(_host.SD_TURBO_DIR_ENV, raising=False)
+    assert _host.load_sd_turbo_base(sd, ["unet", "vae"]) is False and sd == {}
+    monkeypatch.setenv(_host.SD_TURBO_DIR_ENV, str(tmp_path))
+    assert _host.load_sd_turbo_base(sd, ["unet", "vae", "vae_b2a"]) is True
+    assert sd["unet.conv_in.weight"].dtype == torch.float32 and float(sd["unet.conv_in.weight"][0, 0]) == 7.0
+    for pre in ("vae.", "vae_b2a."):                   # both CycleGAN VAEs start from the same SD-Turbo VAE (cyclegan_turbo.py:80)
+        assert float(sd[pre + "encoder.mid_block.attentions.0.to_q.weight"][0, 0]) == 1.0
+        assert float(sd[pre + "encoder.mid_block.attentions.0.to_out.0.bias"][0]) == 2.0
+        assert float(sd[pre + "decoder.conv_out.bias"][0]) == 3.0
+    os.remove(str(tmp_path / "vae" / "diffusion_pytorch_model.safetensors"))
+    assert _host.load_sd_turbo_base({}, ["unet", "vae"]) is False      # partial snapshot is reported, not silently accepted
+
+
 def test_shard_ranges():
     from dist import shard_range
     for B in (1, 7, 8, 64, 128):
