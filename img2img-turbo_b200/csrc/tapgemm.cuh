@@ -29,15 +29,24 @@ constexpr int TG_MAX_STAGES = 8;
 constexpr int TG_MAX_TAPS = 16;
 constexpr int TG_A_STAGE = TG_BM * TG_BK * 2;    // 16 KiB
 constexpr int TG_B_STAGE = 256 * TG_BK * 2;      // 32 KiB (BN <= 256)
+#ifndef I2IT_EPI_WARPS
+#define I2IT_EPI_WARPS 8               // build-time: 8 (default) or 16 (`make EPI16=1`, experimental wide epilogue)
+#endif
+constexpr int TG_EPI_WARPS = I2IT_EPI_WARPS;   // TG_EPI_GROUPS warps per TMEM lane quarter: they take the 32-column rounds in turn
+constexpr int TG_EPI_GROUPS = TG_EPI_WARPS / 4;
+constexpr int TG_EPI_RPW = 8 / TG_EPI_GROUPS;      // rounds per warp at BN = 256
+static_assert(TG_EPI_WARPS == 8 || TG_EPI_WARPS == 16, "epilogue warps: 8 or 16");
 constexpr int TG_BAR_BYTES = 256;
 constexpr int TG_BIAS_BYTES = 2 * 256 * 4;       // per-tile bias slice, double-buffered like the accumulators
 // epilogue store staging: each epilogue warp owns a 32-row x 64-byte tile (XOR-swizzled 16-byte chunks).  A thread holds one
 // accumulator ROW, so direct stores touch 32 different lines per instruction (measured: ~6000 cycles per 128x160 tile, the
 // limiter of every small-K GEMM); through the tile a store instruction writes 8 rows x 64 contiguous bytes instead.
 constexpr int TG_OSTG_WARP = 32 * 64;
-constexpr int TG_OSTG_BYTES = 8 * TG_OSTG_WARP;
-constexpr int TG_SMEM = TG_STAGES * (TG_A_STAGE + TG_B_STAGE) + TG_BAR_BYTES + TG_BIAS_BYTES + TG_OSTG_BYTES + 1024;  // +1024: manual alignment
-constexpr int TG_EPI_WARPS = 8;        // two warps per TMEM lane quarter: they alternate 32-column rounds
+constexpr int TG_OSTG_BYTES = TG_EPI_WARPS * TG_OSTG_WARP;
+// manual 1024-byte alignment slack of the dynamic smem base.  The 16-warp build is 256 B over the 227 KB limit with a full 1 KB
+// of slack, so it budgets 768 B and the kernels trap (error word) if the runtime base needs more (it is 1 KB aligned in practice).
+constexpr int TG_ALIGN_PAD = (TG_EPI_WARPS == 16) ? 768 : 1024;
+constexpr int TG_SMEM = TG_STAGES * (TG_A_STAGE + TG_B_STAGE) + TG_BAR_BYTES + TG_BIAS_BYTES + TG_OSTG_BYTES + TG_ALIGN_PAD;
 constexpr int TG_THREADS = (TG_EPI_WARPS + 2) * 32;   // + TMA producer warp + MMA issuer warp
 constexpr int TG_ACC_COLS = 256;       // TMEM columns per accumulator stage
 
@@ -329,7 +338,7 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const Tile
     for (int cc = warp * 32 + (threadIdx.x & 31); cc < p.BN; cc += TG_EPI_WARPS * 32)
       sb[cc] = (n0 + cc < p.N) ? p.bias[n0 + cc] : 0.f;
   }
-  asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(TG_EPI_WARPS * 32) : "memory");   // the epilogue warps only
   if (stamp) tg_stamp(p, 7);
 
   // Residual reads do not depend on the accumulator: this thread's WHOLE residual slice (its row x the 32-column rounds
@@ -337,11 +346,11 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const Tile
   // (one round of lookahead left the epilogue latency-bound: 0.95 ms vs 0.60 ms for the same conv with/without residual).
   const int nrounds = (p.BN + 31) >> 5;
   const bool res_on = p.res != nullptr && row_ok && p.rcol == 1 && p.act != TG_ACT_GEGLU;
-  uint4 rq[4][4];
-  bool fast[4];
+  uint4 rq[TG_EPI_RPW][4];
+  bool fast[TG_EPI_RPW];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = grp + 2 * i;
+  for (int i = 0; i < TG_EPI_RPW; ++i) {
+    const int r = grp + TG_EPI_GROUPS * i;
     fast[i] = false;
     if (res_on && r < nrounds) {
       const int colg = n0 + 32 * r;
@@ -361,8 +370,8 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const Tile
   const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + acc * TG_ACC_COLS;
 
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = grp + 2 * i;
+  for (int i = 0; i < TG_EPI_RPW; ++i) {
+    const int r = grp + TG_EPI_GROUPS * i;
     if (r >= nrounds) break;                     // warp-uniform
     const int c0 = 32 * r;
     const int nch = min(2, (p.BN - c0) >> 4);
@@ -408,6 +417,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ TapGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (TG_ALIGN_PAD < 1024 && base - smem_u32(smem_raw) > static_cast<uint32_t>(TG_ALIGN_PAD)) {
+    if (threadIdx.x == 0 && p.err) { atomicExch(p.err, 90); __threadfence_system(); }
+    __trap();
+  }
   const int NS = p.stages;
   const uint32_t BST = static_cast<uint32_t>(p.b_stage);
   const uint32_t sA = base;

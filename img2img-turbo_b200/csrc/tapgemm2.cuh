@@ -21,11 +21,12 @@ constexpr int TG2_B_STAGE = 128 * TG_BK * 2;     // half of a BN<=256 weight til
 // 128B-swizzle phase of a tap's view is the same for all of its 8-row groups: base_offset = dx).
 constexpr int TG2_HALO_W = 16, TG2_HALO_H = 18;
 constexpr int TG2_HALO_BYTES = TG2_HALO_H * TG2_HALO_W * TG_BK * 2;   // 36,864
-constexpr int TG2_HALO_STAGES = 3;
+constexpr int TG2_HALO_STAGES = (TG_EPI_WARPS == 16) ? 2 : 3;   // the 16-warp build needs the smem for its staging tiles
 constexpr int TG2_DATA_BYTES = (TG2_STAGES * (TG_A_STAGE + TG2_B_STAGE) > TG2_HALO_STAGES * TG2_HALO_BYTES + TG2_STAGES * TG2_B_STAGE)
                                    ? TG2_STAGES * (TG_A_STAGE + TG2_B_STAGE)
                                    : TG2_HALO_STAGES * TG2_HALO_BYTES + TG2_STAGES * TG2_B_STAGE;
-constexpr int TG2_SMEM = TG2_DATA_BYTES + TG_BAR_BYTES + TG_BIAS_BYTES + TG_OSTG_BYTES + 1024;
+constexpr int TG2_SMEM = TG2_DATA_BYTES + TG_BAR_BYTES + TG_BIAS_BYTES + TG_OSTG_BYTES + TG_ALIGN_PAD;
+static_assert(TG_SMEM <= 232448 && TG2_SMEM <= 232448, "dynamic shared memory per CTA exceeds the 227 KB limit");
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -95,6 +96,10 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmH, const __grid_constant__ TapGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (TG_ALIGN_PAD < 1024 && base - smem_u32(smem_raw) > static_cast<uint32_t>(TG_ALIGN_PAD)) {
+    if (threadIdx.x == 0 && p.err) { atomicExch(p.err, 90); __threadfence_system(); }
+    __trap();
+  }
   // normal mode: [A stages][B stages]; halo mode: [halo stages][B stages]
   const int NS = p.stages;                                  // host-chosen: B stage sized to the real half tile, <= 8 stages
   const uint32_t BST = static_cast<uint32_t>(p.b_stage);
