@@ -504,7 +504,7 @@ void Engine::launch_gemm(Plan& P, const TmapSpec& sa, TmapSpec sb, const TapGemm
   {  // smem ring geometry: B stage = the real (half) tile rounded to the 1024-byte swizzle atom, as many stages as fit
     const int brows = pair ? p.BN / 2 : p.BN;
     p.b_stage = (brows * TG_BK * 2 + 1023) / 1024 * 1024;
-    const int budget = pair ? (p.halo ? TG2_DATA_BYTES - TG2_HALO_STAGES * TG2_HALO_BYTES : TG2_DATA_BYTES) : TG_STAGES * (TG_A_STAGE + TG_B_STAGE);
+    const int budget = pair ? (p.halo ? TG2_DATA_BYTES - TG2_HALO_REGION : TG2_DATA_BYTES) : TG_STAGES * (TG_A_STAGE + TG_B_STAGE);
     const int per = (p.halo ? 0 : TG_A_STAGE) + p.b_stage;
     p.stages = std::max(2, std::min(TG_MAX_STAGES, budget / per));
   }
@@ -593,7 +593,12 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o_in) {
   int tw, th, tn;
   const long long ldo = o.to_io_out_nchw ? 0 : out.ld;
   // halo mode (CTA-pair kernel): 8 x 16 output tiles whose nine taps share one halo tile per k-chunk
-  const bool want_halo = use_halo && use_pair && o.stride == 1 && k == 3 && !sub && !o.x2 && !o.to_io_out_nchw && x.H >= 16 &&
+#ifdef I2IT_HALO_X2
+  const bool halo_x2_ok = true;      // experimental build: the second-source taps ride a small A ring next to the halo stages
+#else
+  const bool halo_x2_ok = !o.x2;
+#endif
+  const bool want_halo = use_halo && use_pair && o.stride == 1 && k == 3 && !sub && halo_x2_ok && !o.to_io_out_nchw && x.H >= 16 &&
                          x.W >= 8 && x.C % 64 == 0;
   if (o.stride == 1) {
     tw = (x.H == 1) ? std::min(128, pow2ceil(x.W)) : std::min(o.to_io_out_nchw ? 32 : 16, pow2ceil(x.W));

@@ -17,14 +17,23 @@ namespace i2it {
 constexpr int TG2_STAGES = 6;
 constexpr int TG2_B_STAGE = 128 * TG_BK * 2;     // half of a BN<=256 weight tile: 16 KiB
 // halo mode (3x3 stride-1 convs): ONE halo tile per k-chunk instead of nine shifted 128-row boxes.  Output tile = 8 wide x 16
-// tall; the halo box is 18 rows x 16 pixels (8 + 2 halo + 6 unused, so that every image row starts a 2048-byte group and the
-// 128B-swizzle phase of a tap's view is the same for all of its 8-row groups: base_offset = dx).
+// tall; the halo box is 18 rows x 16 pixels (8 + 2 halo + 6 unused), so every image row starts a 2048-byte group and a tap's
+// view is "start + dy*2048 + dx*128" with SBO 2048 (swizzle phase from the absolute address, see umma_desc_halo).
 constexpr int TG2_HALO_W = 16, TG2_HALO_H = 18;
 constexpr int TG2_HALO_BYTES = TG2_HALO_H * TG2_HALO_W * TG_BK * 2;   // 36,864
+#ifdef I2IT_HALO_X2
+// experimental (`make HALOX2=1`): halo tiles also for convs with a second source (shortcut / identity / skip K-slab); the extra
+// taps' regular 128-row A boxes go through a small ring of their own next to two halo stages
+constexpr int TG2_HALO_STAGES = 2;
+constexpr int TG2_A2_STAGES = 2;
+#else
 constexpr int TG2_HALO_STAGES = (TG_EPI_WARPS == 16) ? 2 : 3;   // the 16-warp build needs the smem for its staging tiles
-constexpr int TG2_DATA_BYTES = (TG2_STAGES * (TG_A_STAGE + TG2_B_STAGE) > TG2_HALO_STAGES * TG2_HALO_BYTES + TG2_STAGES * TG2_B_STAGE)
+constexpr int TG2_A2_STAGES = 0;
+#endif
+constexpr int TG2_HALO_REGION = TG2_HALO_STAGES * TG2_HALO_BYTES + TG2_A2_STAGES * TG_A_STAGE;   // [halo stages][A2 stages]
+constexpr int TG2_DATA_BYTES = (TG2_STAGES * (TG_A_STAGE + TG2_B_STAGE) > TG2_HALO_REGION + TG2_STAGES * TG2_B_STAGE)
                                    ? TG2_STAGES * (TG_A_STAGE + TG2_B_STAGE)
-                                   : TG2_HALO_STAGES * TG2_HALO_BYTES + TG2_STAGES * TG2_B_STAGE;
+                                   : TG2_HALO_REGION + TG2_STAGES * TG2_B_STAGE;
 constexpr int TG2_SMEM = TG2_DATA_BYTES + TG_BAR_BYTES + TG_BIAS_BYTES + TG_OSTG_BYTES + TG_ALIGN_PAD;
 static_assert(TG_SMEM <= 232448 && TG2_SMEM <= 232448, "dynamic shared memory per CTA exceeds the 227 KB limit");
 
@@ -104,7 +113,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int NS = p.stages;                                  // host-chosen: B stage sized to the real half tile, <= 8 stages
   const uint32_t BST = static_cast<uint32_t>(p.b_stage);
   const uint32_t sA = base;
-  const uint32_t sB = base + (p.halo ? TG2_HALO_STAGES * TG2_HALO_BYTES : NS * TG_A_STAGE);
+  const uint32_t sB = base + (p.halo ? TG2_HALO_REGION : NS * TG_A_STAGE);
   const uint32_t bars = base + TG2_DATA_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (TG_MAX_STAGES + s); };
@@ -113,6 +122,11 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_slot = bars + 8u * (2 * TG_MAX_STAGES + 4);
   auto hfull_bar = [&](int s) { return bars + 8u * (2 * TG_MAX_STAGES + 6 + s); };
   auto hempty_bar = [&](int s) { return bars + 8u * (2 * TG_MAX_STAGES + 6 + TG2_HALO_STAGES + s); };
+#ifdef I2IT_HALO_X2
+  const uint32_t sA2 = base + TG2_HALO_STAGES * TG2_HALO_BYTES;
+  auto a2_empty_bar = [&](int s) { return bars + 8u * (2 * TG_MAX_STAGES + 6 + 2 * TG2_HALO_STAGES + s); };
+  static_assert(8 * (2 * TG_MAX_STAGES + 6 + 2 * TG2_HALO_STAGES + TG2_A2_STAGES) <= TG_BAR_BYTES, "barrier block too small");
+#endif
   float* const s_bias = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + TG_BAR_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -142,6 +156,9 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int s = 0; s < NS; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * TG_EPI_WARPS); }
     for (int s = 0; s < TG2_HALO_STAGES; ++s) { mbar_init(hfull_bar(s), 2); mbar_init(hempty_bar(s), 1); }
+#ifdef I2IT_HALO_X2
+    for (int s = 0; s < TG2_A2_STAGES; ++s) mbar_init(a2_empty_bar(s), 1);
+#endif
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
@@ -165,6 +182,9 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == TG_EPI_WARPS) {
     // ================================ TMA producer (both CTAs) ================================
     int stage = 0, phase = 0, hs = 0, hphase = 0;
+#ifdef I2IT_HALO_X2
+    int s2 = 0, a2phase = 0;
+#endif
     const uint32_t b_bytes = static_cast<uint32_t>(half_bn) * (TG_BK * 2);
     const uint32_t tx_bytes = 2u * (TG_A_STAGE + b_bytes);                                         // both CTAs' bytes
     for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
@@ -210,6 +230,28 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (++stage == NS) { stage = 0; phase ^= 1; }
           }
         }
+#ifdef I2IT_HALO_X2
+        // second-source taps (shortcut / identity / skip K-slab): regular 128-row A boxes through the small A2 ring, B through
+        // the normal ring; both loads of a step complete on the B stage's full barrier
+        for (int t = p.nprim; t < p.num_taps; ++t)
+          for (int kc = 0; kc < p.tap_kc[t]; ++kc) {
+            const CUtensorMap* ta = p.tap_src[t] ? &tmA2 : &tmA;
+            const CUtensorMap* tb = p.tap_src[t] ? &tmB2 : &tmB;
+            mbar_wait(a2_empty_bar(s2), a2phase ^ 1, p.err, 26);
+            mbar_wait(empty_bar(stage), phase ^ 1, p.err, 21);
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(full_bar(stage), tx_bytes);
+              else mbar_arrive_cluster(full_bar(stage), 0);
+              tma_load_5d_2sm(sA2 + s2 * TG_A_STAGE, ta, full_bar(stage), kc * TG_BK + p.tap_a[t][0], a1 + p.tap_a[t][1],
+                              a2 + p.tap_a[t][2], a3 + p.tap_a[t][3], a4 + p.tap_a[t][4]);
+              tma_load_5d_2sm(sB + stage * BST, tb, full_bar(stage), kc * TG_BK + p.tap_b[t][0], n0,
+                              b2 + p.tap_b[t][1], b3 + p.tap_b[t][2], b4 + p.tap_b[t][3]);
+            }
+            __syncwarp();
+            if (++stage == NS) { stage = 0; phase ^= 1; }
+            if (++s2 == TG2_A2_STAGES) { s2 = 0; a2phase ^= 1; }
+          }
+#endif
       } else {
         for (int kc = 0; kc < p.kchunks; ++kc)
           for (int t = 0; t < p.nprim; ++t) load_step(t, kc);
@@ -223,6 +265,9 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ================================ MMA issuer (leader CTA only) ================================
     if (leader) {
       int stage = 0, phase = 0, iter = 0, hs = 0, hphase = 0;
+#ifdef I2IT_HALO_X2
+      int s2 = 0;
+#endif
       for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++iter) {
         const int acc = iter & 1, aphase = (iter >> 1) & 1;
         mbar_wait(tempty_bar(acc), aphase ^ 1, p.err, 22);
@@ -252,6 +297,26 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             if (++hs == TG2_HALO_STAGES) { hs = 0; hphase ^= 1; }
           }
+#ifdef I2IT_HALO_X2
+          for (int t = p.nprim; t < p.num_taps; ++t)
+            for (int kc = 0; kc < p.tap_kc[t]; ++kc, ++s) {
+              mbar_wait(full_bar(stage), phase, p.err, 23);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t adesc = umma_desc_sw128(sA2 + s2 * TG_A_STAGE);
+                const uint64_t bdesc = umma_desc_sw128(sB + stage * BST);
+#pragma unroll
+                for (int k = 0; k < TG_BK / 16; ++k)
+                  tc_mma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, 1u);
+                tc_commit_2sm(empty_bar(stage));
+                tc_commit_2sm(a2_empty_bar(s2));
+                if (s == steps - 1) tc_commit_2sm(tfull_bar(acc));
+              }
+              __syncwarp();
+              if (++stage == NS) { stage = 0; phase ^= 1; }
+              if (++s2 == TG2_A2_STAGES) s2 = 0;
+            }
+#endif
         } else {
           for (int s = 0; s < steps; ++s) {
             mbar_wait(full_bar(stage), phase, p.err, 23);
