@@ -108,10 +108,42 @@ int i2it_forward(i2it_handle* h, const void* x, const void* text_emb, int text_b
   API_END
 }
 
+int i2it_set_text(i2it_handle* h, const void* text_emb, int text_batch, void* stream) {
+  API_BEGIN(h)
+  E.check_device_error();
+  E.set_text(text_emb, text_batch, static_cast<cudaStream_t>(stream));
+  API_END
+}
+
+int i2it_forward_u8(i2it_handle* h, const void* x_u8_hwc, int in_mode, const void* text_emb, int text_batch, const void* eps,
+                    const void* noise_map, float r, void* out_u8_hwc, void* out_latent, int batch, int H, int W, int direction,
+                    void* stream) {
+  API_BEGIN(h)
+  I2IT_CHECK(in_mode >= 0 && in_mode <= 2, "i2it_forward_u8: in_mode must be I2IT_IN_UNIT, I2IT_IN_NORMALIZE or I2IT_IN_SKETCH");
+  I2IT_CHECK(x_u8_hwc && out_u8_hwc, "i2it_forward_u8: null image pointer");
+  IO io;
+  std::memset(&io, 0, sizeof io);
+  io.x_u8 = x_u8_hwc; io.in_mode = in_mode; io.text = text_emb; io.eps = eps; io.noise = noise_map; io.r = r;
+  io.out_u8 = out_u8_hwc; io.out_latent = out_latent;
+  E.check_device_error();
+  E.forward(io, batch, H, W, direction, text_batch, static_cast<cudaStream_t>(stream));
+  API_END
+}
+
+int i2it_prep_launch_count(i2it_handle* h, int* launches) {
+  API_BEGIN(h)
+  I2IT_CHECK(launches != nullptr, "null out pointer");
+  *launches = E.prep_launches_;
+  API_END
+}
+
 int i2it_launch_count(i2it_handle* h, int batch, int H, int W, int direction, int* launches) {
   API_BEGIN(h)
   I2IT_CHECK(launches != nullptr, "null out pointer");
-  *launches = static_cast<int>(E.plan_for(batch, H, W, direction, 1)->ops.size());
+  Plan* P = E.last_plan();
+  const bool match = P && P->key.size() >= 4 && P->key[0] == batch && P->key[1] == H && P->key[2] == W && P->key[3] == direction;
+  if (!match) P = E.plan_for(batch, H, W, direction, 1);
+  *launches = static_cast<int>(P->ops.size());
   API_END
 }
 
@@ -134,6 +166,7 @@ int i2it_read_stage(i2it_handle* h, const char* name, float* dst, size_t dst_ele
 // diagnostic single-op entry points
 // ------------------------------------------------------------------------------------------------
 static void run_plan(Engine& E, Plan& P, cudaStream_t st) {
+  E.flush_prep();
   I2IT_CUDA(cudaDeviceSynchronize());
   for (auto& op : P.ops) op(st);
   cudaError_t e = cudaStreamSynchronize(st);
@@ -169,7 +202,6 @@ int i2it_op_conv2d(i2it_handle* h, const void* x, int N, int H, int W, int Cin, 
     Act ov = view(out, N, Ho, Wo, (act == TG_ACT_GEGLU) ? Cout / 2 : Cout, ldo);
     o.out = &ov;
     E.conv(P, xin, pw, o);
-    I2IT_CUDA(cudaDeviceSynchronize());
     run_plan(E, P, static_cast<cudaStream_t>(stream));
   }
   API_END

@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges show up under Nsight tools, no-ops otherwise
+
 namespace i2it {
 
 static inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
@@ -139,9 +141,9 @@ Engine::Engine(const i2it_config& c) : cfg(c), dtype(c.dtype) {
 
 Engine::~Engine() {
   plans_.clear();
+  textkv_.clear();
   free_prepared();
   for (auto& kv : w_) cudaFree(kv.second.d);
-  if (scratch_) cudaFree(scratch_);
   if (err_host_) cudaFreeHost(err_host_);
   if (gstream_) cudaStreamDestroy(gstream_);
   if (ev_in_) cudaEventDestroy(ev_in_);
@@ -169,6 +171,9 @@ void Engine::free_prepared() {
   prepared_.clear();
   prepared_f32_.clear();
   emb_act_ = nullptr;
+  pending_jobs_.clear();
+  pending_blocks_ = 0;
+  for (auto& g : pending_gemv_) g.clear();
 }
 
 void Engine::set_weight(const std::string& key_in, const void* data, const int64_t* shape, int ndim, int dt, bool is_dev) {
@@ -217,46 +222,86 @@ void Engine::finalize(float lw_unet, float lw_vae, float skip_gamma, float twin_
   I2IT_CUDA(cudaDeviceSynchronize());
   lw_unet_ = lw_unet; lw_vae_ = lw_vae; skip_gamma_ = skip_gamma; twin_r_ = twin_r;
   plans_.clear();
+  textkv_.clear();                 // cached cross-attention operands were projected with the old (LoRA-scaled) weights
   last_plan_ = nullptr;
   free_prepared();
   finalized_ = true;
 }
 
-// acc (fp32 scratch) = c0*W (+ c1*W_other) + sum_adapters s_a * B_a @ A_a
-float* Engine::fold_f32(const std::string& name, long long* numel, float c0, const std::string& other, float c1) {
+// Fold recipe of a layer: c0*W (+ c1*W_other) + sum_adapters s_a * B_a @ A_a — filled into a job, evaluated on device
+void Engine::fill_fold(PrepJob& j, const std::string& name, float c0, const std::string& other, float c1) {
   const WT& w = raw(name, "weight");
-  if (w.numel > scratch_n_) {
-    if (scratch_) cudaFree(scratch_);
-    scratch_n_ = std::max<long long>(w.numel, 1ll << 24);
-    I2IT_CUDA(cudaMalloc(&scratch_, scratch_n_ * sizeof(float)));
-  }
-  const float* w1 = nullptr;
+  j.w0 = w.d; j.c0 = c0; j.w1 = nullptr; j.c1 = 0.f; j.n_adapters = 0;
   if (!other.empty()) {
     const WT& o = raw(other, "weight");
     I2IT_CHECK(o.numel == w.numel, "TwinConv shapes differ");
-    w1 = o.d;
+    j.w1 = o.d; j.c1 = c1;
   }
-  wprep_init_kernel<<<ceil_div(w.numel, 256), 256>>>(scratch_, w.d, c0, w1, c1, w.numel);
   const std::string pre = name + ".lora_A.";
-  for (const auto& kv : w_) {
-    if (kv.first.compare(0, pre.size(), pre) != 0) continue;
-    const std::string rest = kv.first.substr(pre.size());            // "<adapter>.weight"
-    const size_t dot = rest.rfind('.');
-    const std::string adapter = rest.substr(0, dot);
+  std::vector<std::string> adapters;
+  for (const auto& kv : w_)
+    if (kv.first.compare(0, pre.size(), pre) == 0) {
+      const std::string rest = kv.first.substr(pre.size());            // "<adapter>.weight"
+      adapters.push_back(rest.substr(0, rest.rfind('.')));
+    }
+  std::sort(adapters.begin(), adapters.end());                          // fixed summation order
+  for (const auto& adapter : adapters) {
     const float s = adapter_weight(name, adapter);
     if (s == 0.f) continue;
-    const WT& A = kv.second;
+    const WT& A = w_.at(pre + adapter + ".weight");
     auto itb = w_.find(name + ".lora_B." + adapter + ".weight");
     I2IT_CHECK(itb != w_.end(), "lora_A without lora_B for " + name);
     const WT& Bm = itb->second;
     const int rank = static_cast<int>(A.shape[0]);
     const long long inner = A.numel / rank;
     I2IT_CHECK(Bm.shape[0] * inner == w.numel && Bm.shape[1] == rank, "LoRA shape mismatch at " + name);
-    wprep_lora_kernel<<<ceil_div(w.numel, 256), 256>>>(scratch_, A.d, Bm.d, s, rank, inner, w.numel);
+    I2IT_CHECK(j.n_adapters < PREP_MAX_ADAPTERS, "too many LoRA adapters on " + name);
+    j.A[j.n_adapters] = A.d; j.B[j.n_adapters] = Bm.d; j.s[j.n_adapters] = s; j.rank[j.n_adapters] = rank;
+    ++j.n_adapters;
   }
-  I2IT_CUDA(cudaGetLastError());
-  *numel = w.numel;
-  return scratch_;
+}
+
+void Engine::push_job(PrepJob& j) {
+  if (j.n <= 0) return;
+  j.block0 = pending_blocks_;
+  pending_blocks_ += (j.n + PREP_ELEMS_PER_BLOCK - 1) / PREP_ELEMS_PER_BLOCK;
+  pending_jobs_.push_back(j);
+}
+
+void Engine::push_bias_job(float* out, const float* b, const float* add, int cout, int row_off, int half, float c0,
+                           const float* b1, float c1) {
+  PrepJob j;
+  std::memset(&j, 0, sizeof j);
+  j.mode = PREP_BIAS; j.out = out; j.bias = b; j.bias_add = add; j.cout = cout; j.row_off = row_off; j.interleave_half = half;
+  j.c0 = c0; j.w1 = b1; j.c1 = c1;
+  j.n = cout;
+  push_job(j);
+}
+
+// Runs every pending preparation job: <= 3 GEMV launches (time embedding chain) + ONE fold/re-layout launch.
+void Engine::flush_prep() {
+  for (int st = 0; st < 3; ++st) {
+    auto& g = pending_gemv_[st];
+    if (g.empty()) continue;
+    int warps = 0;
+    for (auto& j : g) { j.warp0 = warps; warps += j.out; }
+    GemvJob* d = static_cast<GemvJob*>(dmalloc(g.size() * sizeof(GemvJob)));
+    I2IT_CUDA(cudaMemcpy(d, g.data(), g.size() * sizeof(GemvJob), cudaMemcpyHostToDevice));
+    gemv_jobs_kernel<<<ceil_div(warps * 32ll, 256), 256>>>(d, static_cast<int>(g.size()));
+    I2IT_CUDA(cudaGetLastError());
+    prep_launches_ += 1;
+    g.clear();
+  }
+  if (!pending_jobs_.empty()) {
+    PrepJob* d = static_cast<PrepJob*>(dmalloc(pending_jobs_.size() * sizeof(PrepJob)));
+    I2IT_CUDA(cudaMemcpy(d, pending_jobs_.data(), pending_jobs_.size() * sizeof(PrepJob), cudaMemcpyHostToDevice));
+    I2IT_CHECK(pending_blocks_ < (1ll << 31), "weight preparation: too many blocks for one launch");
+    DISPATCH_T(dtype, (prep_jobs_kernel<T><<<static_cast<unsigned>(pending_blocks_), 256>>>(d, static_cast<int>(pending_jobs_.size()))));
+    I2IT_CUDA(cudaGetLastError());
+    prep_launches_ += 1;
+    pending_jobs_.clear();
+    pending_blocks_ = 0;
+  }
 }
 
 PW Engine::prep(const std::string& cache_key, const std::vector<std::string>& names, bool geglu, float scale,
@@ -279,27 +324,21 @@ PW Engine::prep(const std::string& cache_key, const std::vector<std::string>& na
   I2IT_CHECK(!geglu || names.size() == 1, "GEGLU interleave applies to a single projection");
   const size_t wbytes = static_cast<size_t>(pw.taps) * pw.rows * pw.cin_pad * 2;
   pw.w = static_cast<uint16_t*>(dmalloc(wbytes));
-  if (any_bias) {
-    pw.bias = static_cast<float*>(dmalloc(pw.rows * sizeof(float)));
-    I2IT_CUDA(cudaMemset(pw.bias, 0, pw.rows * sizeof(float)));
-  }
+  if (any_bias) pw.bias = static_cast<float*>(dmalloc(pw.rows * sizeof(float)));
   int row_off = 0;
   for (const auto& n : names) {
-    long long numel = 0;
-    float* acc = fold_f32(n, &numel);
     const int cout = static_cast<int>(raw(n, "weight").shape[0]);
-    const long long total = static_cast<long long>(cout) * pw.cin_pad * pw.taps;
     const int half = geglu ? cout / 2 : 0;
-    DISPATCH_T(dtype, (wprep_store_kernel<T><<<ceil_div(total, 256), 256>>>(
-                          acc, reinterpret_cast<T*>(pw.w), cout, pw.cin, pw.taps, pw.cin_pad, pw.rows, row_off, half,
-                          scale, total)));
-    if (pw.bias) {
-      const float* b = has(n + ".bias") ? raw(n, "bias").d : nullptr;
-      bias_store_kernel<<<ceil_div(cout, 256), 256>>>(b, pw.bias, cout, row_off, half, bias_add);
-    }
+    PrepJob j;
+    std::memset(&j, 0, sizeof j);
+    fill_fold(j, n);
+    j.mode = PREP_STORE; j.out = pw.w; j.cout = cout; j.cin = pw.cin; j.taps = pw.taps; j.cin_pad = pw.cin_pad;
+    j.rows_total = pw.rows; j.row_off = row_off; j.interleave_half = half; j.scale = scale;
+    j.n = static_cast<long long>(cout) * pw.cin_pad * pw.taps;
+    push_job(j);
+    if (pw.bias) push_bias_job(pw.bias, has(n + ".bias") ? raw(n, "bias").d : nullptr, bias_add, cout, row_off, half);
     row_off += cout;
   }
-  I2IT_CUDA(cudaGetLastError());
   prepared_[cache_key] = pw;
   return pw;
 }
@@ -318,14 +357,14 @@ PW Engine::prep_twin(const std::string& pre, const std::string& cur, float r) {
   pw.cin_pad = round_up(pw.cin, 8);
   pw.w = static_cast<uint16_t*>(dmalloc(static_cast<size_t>(pw.taps) * pw.rows * pw.cin_pad * 2));
   pw.bias = static_cast<float*>(dmalloc(pw.rows * sizeof(float)));
-  long long numel = 0;
-  float* acc = fold_f32(pre, &numel, 1.f - r, cur, r);
-  const long long total = static_cast<long long>(pw.rows) * pw.cin_pad * pw.taps;
-  DISPATCH_T(dtype, (wprep_store_kernel<T><<<ceil_div(total, 256), 256>>>(acc, reinterpret_cast<T*>(pw.w), pw.rows, pw.cin,
-                                                                         pw.taps, pw.cin_pad, pw.rows, 0, 0, 1.f, total)));
-  // bias = (1-r) b_pre + r b_cur
-  wprep_init_kernel<<<ceil_div(pw.rows, 256), 256>>>(pw.bias, raw(pre, "bias").d, 1.f - r, raw(cur, "bias").d, r, pw.rows);
-  I2IT_CUDA(cudaGetLastError());
+  PrepJob j;
+  std::memset(&j, 0, sizeof j);
+  fill_fold(j, pre, 1.f - r, cur, r);                       // W = (1-r) W_pre + r W_cur   (pix2pix_turbo.py:23-26)
+  j.mode = PREP_STORE; j.out = pw.w; j.cout = pw.rows; j.cin = pw.cin; j.taps = pw.taps; j.cin_pad = pw.cin_pad;
+  j.rows_total = pw.rows; j.scale = 1.f;
+  j.n = static_cast<long long>(pw.rows) * pw.cin_pad * pw.taps;
+  push_job(j);
+  push_bias_job(pw.bias, raw(pre, "bias").d, nullptr, pw.rows, 0, 0, 1.f - r, raw(cur, "bias").d, r);   // (1-r) b_pre + r b_cur
   prepared_[key] = pw;
   return pw;
 }
@@ -340,12 +379,13 @@ PW Engine::prep_im2col3(const std::string& name) {
   pw.rows = static_cast<int>(w0.shape[0]); pw.cin = 32; pw.cin_pad = 32; pw.taps = 1;
   pw.w = static_cast<uint16_t*>(dmalloc(static_cast<size_t>(pw.rows) * 32 * 2));
   pw.bias = static_cast<float*>(dmalloc(pw.rows * sizeof(float)));
-  long long numel = 0;
-  float* acc = fold_f32(name, &numel);
-  DISPATCH_T(dtype, (wprep_store_im2col_kernel<T><<<ceil_div(pw.rows * 32, 256), 256>>>(acc, reinterpret_cast<T*>(pw.w), pw.rows)));
-  I2IT_CUDA(cudaMemset(pw.bias, 0, pw.rows * sizeof(float)));
-  bias_store_kernel<<<ceil_div(pw.rows, 256), 256>>>(raw(name, "bias").d, pw.bias, pw.rows, 0, 0, nullptr);
-  I2IT_CUDA(cudaGetLastError());
+  PrepJob j;
+  std::memset(&j, 0, sizeof j);
+  fill_fold(j, name);
+  j.mode = PREP_IM2COL3; j.out = pw.w; j.cout = pw.rows; j.cin = 3; j.taps = 9; j.scale = 1.f;
+  j.n = static_cast<long long>(pw.rows) * 32;
+  push_job(j);
+  push_bias_job(pw.bias, raw(name, "bias").d, nullptr, pw.rows, 0, 0);
   prepared_[key] = pw;
   return pw;
 }
@@ -357,8 +397,10 @@ PW Engine::prep_identity(int n) {
   PW pw;
   pw.rows = n; pw.cin = n; pw.cin_pad = n; pw.taps = 1;
   pw.w = static_cast<uint16_t*>(dmalloc(static_cast<size_t>(n) * n * 2));
-  DISPATCH_T(dtype, (identity_store_kernel<T><<<ceil_div(1ll * n * n, 256), 256>>>(reinterpret_cast<T*>(pw.w), n)));
-  I2IT_CUDA(cudaGetLastError());
+  PrepJob j;
+  std::memset(&j, 0, sizeof j);
+  j.mode = PREP_IDENTITY; j.out = pw.w; j.cout = n; j.n = static_cast<long long>(n) * n;
+  push_job(j);
   prepared_[key] = pw;
   return pw;
 }
@@ -374,13 +416,13 @@ PW Engine::prep_subpixel(const std::string& name) {
   const long long total = 16ll * pw.rows * pw.cin_pad;
   pw.w = static_cast<uint16_t*>(dmalloc(static_cast<size_t>(total) * 2));
   pw.bias = static_cast<float*>(dmalloc(pw.rows * sizeof(float)));
-  long long numel = 0;
-  float* acc = fold_f32(name, &numel);
-  DISPATCH_T(dtype, (wprep_store_subpixel_kernel<T><<<ceil_div(total, 256), 256>>>(acc, reinterpret_cast<T*>(pw.w), pw.rows, pw.cin,
-                                                                                  pw.cin_pad, total)));
-  I2IT_CUDA(cudaMemset(pw.bias, 0, pw.rows * sizeof(float)));
-  bias_store_kernel<<<ceil_div(pw.rows, 256), 256>>>(raw(name, "bias").d, pw.bias, pw.rows, 0, 0, nullptr);
-  I2IT_CUDA(cudaGetLastError());
+  PrepJob j;
+  std::memset(&j, 0, sizeof j);
+  fill_fold(j, name);
+  j.mode = PREP_SUBPIXEL; j.out = pw.w; j.cout = pw.rows; j.cin = pw.cin; j.taps = 9; j.cin_pad = pw.cin_pad; j.scale = 1.f;
+  j.n = total;
+  push_job(j);
+  push_bias_job(pw.bias, raw(name, "bias").d, nullptr, pw.rows, 0, 0);
   prepared_[key] = pw;
   return pw;
 }
@@ -412,6 +454,17 @@ const float* Engine::temb_bias(const std::string& p) {
   auto it = prepared_f32_.find(key);
   if (it != prepared_f32_.end()) return it->second;
   const int T = cfg.temb_dim, C0 = cfg.unet_channels[0];
+  auto gemv = [&](int stage, const std::string& name, const float* x, float* y, int out, int in, int silu) {
+    PrepJob f;
+    std::memset(&f, 0, sizeof f);
+    fill_fold(f, name);
+    GemvJob g;
+    std::memset(&g, 0, sizeof g);
+    g.w = f.w0; g.b = raw(name, "bias").d; g.x = x; g.y = y; g.out = out; g.in = in; g.silu_out = silu;
+    g.n_adapters = f.n_adapters;
+    for (int a = 0; a < f.n_adapters; ++a) { g.A[a] = f.A[a]; g.B[a] = f.B[a]; g.s[a] = f.s[a]; g.rank[a] = f.rank[a]; }
+    pending_gemv_[stage].push_back(g);
+  };
   if (!emb_act_) {
     // Timesteps(flip_sin_to_cos=True, freq_shift=0) at t = 999, then TimestepEmbedding, then the SiLU every resnet applies
     std::vector<float> te(C0);
@@ -425,19 +478,13 @@ const float* Engine::temb_bias(const std::string& p) {
     float* d_h = static_cast<float*>(dmalloc(T * sizeof(float)));
     emb_act_ = static_cast<float*>(dmalloc(T * sizeof(float)));
     I2IT_CUDA(cudaMemcpy(d_te, te.data(), C0 * sizeof(float), cudaMemcpyHostToDevice));
-    long long n = 0;
-    float* W1 = fold_f32("unet.time_embedding.linear_1", &n);
-    gemv_kernel<<<ceil_div(T * 32ll, 256), 256>>>(W1, raw("unet.time_embedding.linear_1", "bias").d, d_te, d_h, T, C0, 1);
-    float* W2 = fold_f32("unet.time_embedding.linear_2", &n);
-    gemv_kernel<<<ceil_div(T * 32ll, 256), 256>>>(W2, raw("unet.time_embedding.linear_2", "bias").d, d_h, emb_act_, T, T, 1);
+    gemv(0, "unet.time_embedding.linear_1", d_te, d_h, T, C0, 1);
+    gemv(1, "unet.time_embedding.linear_2", d_h, emb_act_, T, T, 1);
   }
   const WT& w = raw(p + ".time_emb_proj", "weight");
   const int cout = static_cast<int>(w.shape[0]);
   float* out = static_cast<float*>(dmalloc(cout * sizeof(float)));
-  long long n = 0;
-  float* W = fold_f32(p + ".time_emb_proj", &n);
-  gemv_kernel<<<ceil_div(cout * 32ll, 256), 256>>>(W, raw(p + ".time_emb_proj", "bias").d, emb_act_, out, cout, T, 0);
-  I2IT_CUDA(cudaGetLastError());
+  gemv(2, p + ".time_emb_proj", emb_act_, out, cout, T, 0);
   prepared_f32_[key] = out;
   return out;
 }
@@ -1036,11 +1083,39 @@ Act Engine::flash_attention(Plan& P, const Act& q, const Act& k, const Act& vt, 
 // ---------------------------------------------------------------------------------------------
 // executor
 // ---------------------------------------------------------------------------------------------
-void Engine::forward(const IO& io, int B, int H, int W, int direction, int text_batch, cudaStream_t st) {
+void Engine::set_text(const void* text, int text_batch, cudaStream_t st) {
+  I2IT_CHECK(finalized_, "i2it_finalize_weights must be called before i2it_set_text");
+  I2IT_CHECK(text != nullptr && text_batch > 0, "i2it_set_text: null text embedding");
+  auto& slot = textkv_[text_batch];
+  if (!slot) {
+    slot.reset(new TextKV());
+    slot->text_batch = text_batch;
+    build_text_kv(*slot);
+  }
+  TextKV& T = *slot;
+  T.plan.io.text = text;
+  nvtxRangePushA("i2it:text_kv");
+  g_pdl.enabled = false; g_pdl.prev_is_kernel = false;
+  for (auto& op : T.plan.ops) op(st);
+  nvtxRangePop();
+  I2IT_CUDA(cudaGetLastError());
+  T.filled = true;
+}
+
+void Engine::forward(const IO& io_in, int B, int H, int W, int direction, int text_batch, cudaStream_t st) {
   I2IT_CHECK(H % 64 == 0 && W % 64 == 0 && H > 0 && W > 0, "H and W must be positive multiples of 64");
   I2IT_CHECK(B > 0 && (text_batch == 1 || text_batch == B), "text_batch must be 1 or batch");
-  I2IT_CHECK(io.x && io.text && io.eps && io.out, "null input/output pointer");
-  Plan* P = plan_for(B, H, W, direction, text_batch);
+  IO io = io_in;
+  const int io_mode = (io.x_u8 ? IO_U8_IN : 0) | (io.out_u8 ? IO_U8_OUT : 0);
+  I2IT_CHECK((io.x || io.x_u8) && io.eps && (io.out || io.out_u8), "null input/output pointer");
+  const bool text_cached = io.text == nullptr;
+  if (text_cached) {
+    auto it = textkv_.find(text_batch);
+    I2IT_CHECK(it != textkv_.end() && it->second->filled,
+               "text_emb == NULL: call i2it_set_text first (and again after every i2it_finalize_weights)");
+  }
+  Plan* P = plan_for(B, H, W, direction, text_batch, text_cached, io_mode);
+  if (io_mode & IO_U8_OUT) io.out = P->u8_out_tmp;
   P->io = io;
   last_plan_ = P;
   if (cfg.use_cuda_graph) {
@@ -1062,12 +1137,25 @@ void Engine::forward(const IO& io, int B, int H, int W, int direction, int text_
       cudaGraphDestroy(g);
       P->graphs.emplace_back(io, ge);
     }
+    nvtxRangePushA("i2it:forward(graph)");
     I2IT_CUDA(cudaGraphLaunch(ge, gstream_));
+    nvtxRangePop();
     I2IT_CUDA(cudaEventRecord(ev_out_, gstream_));
     I2IT_CUDA(cudaStreamWaitEvent(st, ev_out_, 0));
   } else {
     g_pdl.enabled = use_pdl; g_pdl.prev_is_kernel = false;
-    for (auto& op : P->ops) op(st);
+    size_t next_range = 0;
+    bool open = false;
+    for (size_t i = 0; i < P->ops.size(); ++i) {
+      if (next_range < P->ranges.size() && P->ranges[next_range].first == i) {   // NVTX: vae_encode / unet / ddpm_step / vae_decode
+        if (open) nvtxRangePop();
+        nvtxRangePushA((std::string("i2it:") + P->ranges[next_range].second).c_str());
+        open = true;
+        ++next_range;
+      }
+      P->ops[i](st);
+    }
+    if (open) nvtxRangePop();
     I2IT_CUDA(cudaGetLastError());
   }
   if (trace_on) dump_trace(*P, st);

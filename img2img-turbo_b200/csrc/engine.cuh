@@ -11,6 +11,7 @@
 
 #include "../../include/i2it.h"
 #include "kernels.cuh"
+#include "prep.cuh"
 #include "tapgemm.cuh"
 #include "flash.cuh"
 #include "tapgemm2.cuh"
@@ -87,8 +88,12 @@ struct NormW { const float* g = nullptr; const float* b = nullptr; int C = 0; };
 struct IO {
   const void* x = nullptr; const void* text = nullptr; const void* eps = nullptr; const void* noise = nullptr;
   float r = 1.f; void* out = nullptr; void* out_latent = nullptr;
+  const void* x_u8 = nullptr; void* out_u8 = nullptr;   // uint8 HWC boundary (i2it_forward_u8): x / out then point at internal buffers
+  int in_mode = 0;                                      // u8 input transform (see pack_input_im2col_u8_kernel)
+  int pad_ = 0;
   bool operator==(const IO& o) const { return std::memcmp(this, &o, sizeof(IO)) == 0; }
 };
+enum IoMode : int { IO_U8_IN = 1, IO_U8_OUT = 2 };
 
 struct OpMeta {                  // bookkeeping for i2it_profile / bench roofline accounting
   std::string kind;              // "tapgemm:conv3x3", "gn_apply", ...
@@ -104,6 +109,9 @@ struct Plan {
   struct Trace { unsigned long long* buf; int grid; std::string what; };
   std::vector<Trace> traces;                           // I2IT_TRACE=1 only
   std::vector<std::shared_ptr<void>> keep;
+  std::vector<int> key;                                // (B, H, W, direction, text_batch, text_cached, io_mode)
+  void* u8_out_tmp = nullptr;                          // NCHW image the last conv writes when the caller wants uint8 HWC
+  std::vector<std::pair<size_t, const char*>> ranges;  // (first op index, name): NVTX stage ranges of the eager path
   IO io;
   std::vector<std::pair<IO, cudaGraphExec_t>> graphs;  // small cache: one instantiated graph per distinct IO pointer set
   ~Plan() { for (auto& g : graphs) cudaGraphExecDestroy(g.second); }
@@ -132,6 +140,15 @@ struct WT {                      // raw fp32 tensor of the state dict, on device
   long long numel = 0;
 };
 
+// cached cross-attention operands of one prompt batch: K [tb*77, C] and V^T [tb][C][80] per transformer block
+struct TextKV {
+  Plan plan;                                   // declared first: its pool outlives the Acts below
+  Act text;
+  std::map<std::string, std::pair<Act, Act>> kv;   // transformer-block prefix -> (K, V^T)
+  int text_batch = 0;
+  bool filled = false;
+};
+
 class Engine {
  public:
   explicit Engine(const i2it_config& c);
@@ -143,8 +160,11 @@ class Engine {
   void set_weight(const std::string& key, const void* data, const int64_t* shape, int ndim, int dt, bool is_dev);
   void set_adapter_scale(const std::string& a, float s) { adapter_scale_[a] = s; }
   void finalize(float lw_unet, float lw_vae, float skip_gamma, float twin_r);
-  Plan* plan_for(int B, int H, int W, int direction, int text_batch);
+  Plan* plan_for(int B, int H, int W, int direction, int text_batch, bool text_cached = false, int io_mode = 0);
   void forward(const IO& io, int B, int H, int W, int direction, int text_batch, cudaStream_t st);
+  // cross-attention K / V^T of the prompt, computed once per prompt (i2it_set_text) instead of once per forward
+  void set_text(const void* text, int text_batch, cudaStream_t st);
+  Plan* last_plan() const { return last_plan_; }
   void read_stage(const std::string& name, float* dst, size_t dst_elems, int dims[4]);
 
   // ---- op builders (append launches to a plan) ----
@@ -177,10 +197,14 @@ class Engine {
   NormW norm(const std::string& name);
   const float* temb_bias(const std::string& resnet_prefix);          // time_emb_proj(silu(emb)) at t=999
   void free_prepared();
+  void flush_prep();                                                // run all pending preparation jobs (4-5 launches)
+  int prep_launches_ = 0;
 
   // ---- model graph ----
-  Act build_vae_encoder(Plan& P, const std::string& vp, int B, int H, int W, std::vector<Act>& skips);
-  Act build_unet(Plan& P, const Act& z, int text_batch);
+  Act build_vae_encoder(Plan& P, const std::string& vp, int B, int H, int W, std::vector<Act>& skips, bool u8_in = false);
+  Act build_unet(Plan& P, const Act& z, int text_batch, bool text_cached);
+  void build_text_kv(struct TextKV& T);
+  std::vector<std::string> xformer_prefixes() const;
   void build_vae_decoder(Plan& P, const std::string& vp, const Act& dec_in, std::vector<Act>& skips);
   Act vae_resnet(Plan& P, const std::string& p, const Act& x, const Act* skip = nullptr, const PW* skip_w = nullptr);
   Act vae_attn(Plan& P, const std::string& p, const Act& x);
@@ -218,14 +242,20 @@ class Engine {
   std::unordered_map<std::string, PW> prepared_;
   std::unordered_map<std::string, float*> prepared_f32_;
   std::vector<void*> prep_allocs_;
-  float* scratch_ = nullptr; long long scratch_n_ = 0;
   float* emb_act_ = nullptr;
+  std::vector<PrepJob> pending_jobs_;
+  std::vector<GemvJob> pending_gemv_[3];
+  long long pending_blocks_ = 0;
+  void fill_fold(PrepJob& j, const std::string& name, float c0 = 1.f, const std::string& other = "", float c1 = 0.f);
+  void push_job(PrepJob& j);
+  void push_bias_job(float* out, const float* b, const float* add, int cout, int row_off, int half, float c0 = 1.f,
+                     const float* b1 = nullptr, float c1 = 0.f);
+  std::map<int, std::unique_ptr<struct TextKV>> textkv_;   // by text_batch
   std::map<std::vector<int>, std::unique_ptr<Plan>> plans_;
   Plan* last_plan_ = nullptr;
   Act text_;                     // staged text embedding while a UNet plan is being built
+  TextKV* text_kv_ = nullptr;    // ... or the cached cross-attention operands (text_emb == NULL forwards)
 
-  float* fold_f32(const std::string& name, long long* numel, float c0 = 1.f, const std::string& other = "",
-                  float c1 = 0.f);
   float adapter_weight(const std::string& name, const std::string& adapter) const;
   void* dmalloc(size_t bytes);
 };

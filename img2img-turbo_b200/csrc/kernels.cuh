@@ -300,6 +300,63 @@ __global__ void pack_input_im2col_kernel(const T* __restrict__ x, T* __restrict_
                                         Elem<T>::pack(v[8 * g + 4], v[8 * g + 5]), Elem<T>::pack(v[8 * g + 6], v[8 * g + 7])));
 }
 
+// uint8 HWC boundary.  Input: what the reference CLIs do on the host before the forward —
+//   mode 0  F.to_tensor(img)                      v = u8/255                      (/root/reference/src/inference_paired.py:50)
+//   mode 1  ToTensor + Normalize([0.5],[0.5])     v = (u8/255 - 0.5)/0.5          (/root/reference/src/inference_unpaired.py:45-47)
+//   mode 2  (F.to_tensor(img) < 0.5).float()      v = u8/255 < 0.5 ? 1 : 0        (/root/reference/src/inference_paired.py:56-57)
+// in fp32 followed by the .half()/.to(dtype) rounding — fused with the im2col packing of encoder.conv_in.
+__device__ __forceinline__ float u8_to_input(uint8_t q, int mode) {
+  const float v = static_cast<float>(q) / 255.0f;
+  if (mode == 1) return (v - 0.5f) / 0.5f;
+  if (mode == 2) return v < 0.5f ? 1.0f : 0.0f;
+  return v;
+}
+template <typename T>
+__global__ void pack_input_im2col_u8_kernel(const uint8_t* __restrict__ x /*[B,H,W,3]*/, T* __restrict__ y, int H, int W,
+                                            long long total, int mode) {
+  pdl_sync();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // over B*H*W pixels
+  if (i >= total) return;
+  const long long HW = static_cast<long long>(H) * W;
+  const long long n = i / HW;
+  const int p = static_cast<int>(i % HW), py = p / W, px = p % W;
+  float v[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int yy = py + ky - 1, xx = px + kx - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        const uint8_t* q = x + ((n * H + yy) * W + xx) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[(ky * 3 + kx) * 3 + c] = Elem<T>::to_f(Elem<T>::from_f(u8_to_input(q[c], mode)));
+      }
+    }
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    st16(y + i * 32 + g * 8, make_uint4(Elem<T>::pack(v[8 * g], v[8 * g + 1]), Elem<T>::pack(v[8 * g + 2], v[8 * g + 3]),
+                                        Elem<T>::pack(v[8 * g + 4], v[8 * g + 5]), Elem<T>::pack(v[8 * g + 6], v[8 * g + 7])));
+}
+// Output: transforms.ToPILImage()(output_image[0].cpu() * 0.5 + 0.5)  (/root/reference/src/inference_paired.py:72,
+// /root/reference/src/inference_unpaired.py:53): three ops in the activation dtype (x*0.5, +0.5, .mul(255)), each rounded, then
+// .byte() (truncation).  NCHW [B,3,H,W] -> HWC uint8 [B,H,W,3].
+template <typename T>
+__global__ void nchw_to_u8hwc_kernel(const T* __restrict__ x, uint8_t* __restrict__ y, long long HW, long long total) {
+  pdl_sync();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // over B*H*W pixels
+  if (i >= total) return;
+  const long long n = i / HW, p = i % HW;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float a = Elem<T>::to_f(Elem<T>::from_f(Elem<T>::to_f(x[(n * 3 + c) * HW + p]) * 0.5f));
+    const float b = Elem<T>::to_f(Elem<T>::from_f(a + 0.5f));
+    const float d = Elem<T>::to_f(Elem<T>::from_f(b * 255.0f));
+    y[i * 3 + c] = static_cast<uint8_t>(fminf(fmaxf(d, 0.f), 255.f));
+  }
+}
+
 // DiagonalGaussianDistribution.sample() * scaling_factor (+ the stochastic blend of
 // /root/reference/src/pix2pix_turbo.py:210): moments NHWC (ld) -> latent NHWC8 (channels 4..7 zero).
 template <typename T>
@@ -329,22 +386,36 @@ __global__ void latent_sample_kernel(const T* __restrict__ mom, int ldm, const T
 }
 
 // DDPMScheduler.step closed form at t=999 and the `/ scaling_factor` feeding vae.decode
-// (/root/reference/src/pix2pix_turbo.py:200-203): x0 = (x - s1*eps_hat)/sa, fp32 math, one rounding.
+// (/root/reference/src/pix2pix_turbo.py:200-203): x0 = (x - s1*eps_hat)/sa.
+//   three_round == 0  Pix2Pix_Turbo: `timesteps` is a 1-D tensor, so alphas_cumprod[t] is a dimensioned fp32 tensor and the
+//                     whole step is promoted to fp32, then rounded once by .to(model_pred.dtype)  (pix2pix_turbo.py:162,200-201)
+//   three_round == 1  CycleGAN_Turbo: `timesteps[i]` is 0-dim, alphas_cumprod[t] is a 0-dim CPU fp32 tensor, so every op stays
+//                     in the activation dtype with fp32 op-math: round(s1*e), round(x - .), round(. * (1/sa))  — torch's CUDA
+//                     mul/div kernels take a CPU scalar operand in fp32 and divide by multiplying with the fp32 reciprocal
+//                     (/root/reference/src/cyclegan_turbo.py:205); tests/test_gpu_e2e.py checks this bit for bit against torch.
 template <typename T>
 __global__ void ddpm_step_kernel(const T* __restrict__ zin /*NHWC8*/, const T* __restrict__ pred, int ldp,
                                  float s1, float sa, float inv_sf, T* __restrict__ dec_in /*NHWC8*/,
-                                 T* __restrict__ x0_nchw /*nullable*/, long long HW, long long total) {
+                                 T* __restrict__ x0_nchw /*nullable*/, long long HW, long long total, int three_round) {
   pdl_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const long long n = i / HW, p = i % HW;
+  const float inv_sa = 1.0f / sa;
   float o[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    const float x0 = (Elem<T>::to_f(zin[i * 8 + c]) - s1 * Elem<T>::to_f(pred[i * ldp + c])) / sa;
-    const float x0r = Elem<T>::to_f(Elem<T>::from_f(x0));        // x_denoised.to(dtype)
-    if (x0_nchw) x0_nchw[(n * 4 + c) * HW + p] = Elem<T>::from_f(x0);
-    o[c] = x0r * inv_sf;
+    const float x = Elem<T>::to_f(zin[i * 8 + c]), e = Elem<T>::to_f(pred[i * ldp + c]);
+    T x0t;
+    if (three_round) {
+      const float t1 = Elem<T>::to_f(Elem<T>::from_f(s1 * e));
+      const float t2 = Elem<T>::to_f(Elem<T>::from_f(x - t1));
+      x0t = Elem<T>::from_f(t2 * inv_sa);
+    } else {
+      x0t = Elem<T>::from_f((x - s1 * e) / sa);                  // x_denoised.to(dtype)
+    }
+    if (x0_nchw) x0_nchw[(n * 4 + c) * HW + p] = x0t;
+    o[c] = Elem<T>::to_f(x0t) * inv_sf;
   }
   st16(dec_in + i * 8, make_uint4(Elem<T>::pack(o[0], o[1]), Elem<T>::pack(o[2], o[3]), 0u, 0u));
 }
@@ -377,106 +448,5 @@ __global__ void copy2d_kernel(const T* __restrict__ x, int ldx, T* __restrict__ 
   const int v = static_cast<int>(i % vecs);
   st16(y + r * ldy + v * 8, ld_nc16(x + r * ldx + v * 8));
 }
-
-// =============================================================================================
-// load-time weight preparation (fp32 math, one rounding) — replaces ~1000 runtime peft LoRA kernels
-// =============================================================================================
-// acc[i] = c0*w0[i] (+ c1*w1[i])        (TwinConv blend: /root/reference/src/pix2pix_turbo.py:23-26)
-static __global__ void wprep_init_kernel(float* __restrict__ acc, const float* __restrict__ w0, float c0,
-                                  const float* __restrict__ w1, float c1, long long n) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) acc[i] = c0 * w0[i] + (w1 ? c1 * w1[i] : 0.f);
-}
-// acc[o][j] += s * sum_r B[o][r] * A[r][j]   (peft get_delta_weight for Linear and Conv2d; j = flattened cin*kh*kw)
-static __global__ void wprep_lora_kernel(float* __restrict__ acc, const float* __restrict__ A, const float* __restrict__ Bm,
-                                  float s, int rank, long long inner, long long n) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const long long o = i / inner, j = i % inner;
-  float d = 0.f;
-  for (int r = 0; r < rank; ++r) d += Bm[o * rank + r] * A[r * inner + j];
-  acc[i] += s * d;
-}
-// acc [Cout][Cin][taps] fp32 -> out[tap][row_map(o)][cin_pad] in T (zero padded); row_map handles the GEGLU
-// interleave and the row offset of fused projections.
-template <typename T>
-__global__ void wprep_store_kernel(const float* __restrict__ acc, T* __restrict__ out, int cout, int cin, int taps,
-                                   int cin_pad, int rows_total, int row_off, int interleave_half, float scale,
-                                   long long n /* cout*cin_pad*taps */) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int ci = static_cast<int>(i % cin_pad);
-  long long r = i / cin_pad;
-  const int o = static_cast<int>(r % cout);
-  const int t = static_cast<int>(r / cout);
-  int orow = o;
-  if (interleave_half > 0) orow = (o < interleave_half) ? 2 * o : 2 * (o - interleave_half) + 1;
-  orow += row_off;
-  const float v = (ci < cin) ? acc[(static_cast<long long>(o) * cin + ci) * taps + t] * scale : 0.f;
-  out[(static_cast<long long>(t) * rows_total + orow) * cin_pad + ci] = Elem<T>::from_f(v);
-}
-// nearest-2x upsample followed by a 3x3 pad-1 conv == four 2x2 convs on the LOW-RES tensor, one per output parity
-// (py,px), with pre-summed taps:  rows R(0,0)={0} R(0,1)={1,2} R(1,0)={0,1} R(1,1)={2}  (same for columns).
-// acc [Cout][Cin][9] fp32 -> out[phase*4 + ty*2+tx][Cout][cin_pad], phase = py*2+px.  Summed in fp32, rounded once.
-template <typename T>
-__global__ void wprep_store_subpixel_kernel(const float* __restrict__ acc, T* __restrict__ out, int cout, int cin,
-                                            int cin_pad, long long n /* 16*cout*cin_pad */) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int ci = static_cast<int>(i % cin_pad);
-  long long r = i / cin_pad;
-  const int o = static_cast<int>(r % cout);
-  const int t16 = static_cast<int>(r / cout);
-  const int phase = t16 >> 2, ty = (t16 >> 1) & 1, tx = t16 & 1, py = phase >> 1, px = phase & 1;
-  float v = 0.f;
-  if (ci < cin) {
-    const int ky0 = (py == 0) ? (ty == 0 ? 0 : 1) : (ty == 0 ? 0 : 2), ky1 = (py == 0) ? (ty == 0 ? 0 : 2) : (ty == 0 ? 1 : 2);
-    const int kx0 = (px == 0) ? (tx == 0 ? 0 : 1) : (tx == 0 ? 0 : 2), kx1 = (px == 0) ? (tx == 0 ? 0 : 2) : (tx == 0 ? 1 : 2);
-    const float* w = acc + (static_cast<long long>(o) * cin + ci) * 9;
-    for (int ky = ky0; ky <= ky1; ++ky)
-      for (int kx = kx0; kx <= kx1; ++kx) v += w[ky * 3 + kx];
-  }
-  out[i] = Elem<T>::from_f(v);
-}
-
-// acc [Cout][3][9] fp32 (3x3 conv over 3 channels) -> out[Cout][32] with k = tap*3 + c (matches pack_input_im2col_kernel)
-template <typename T>
-__global__ void wprep_store_im2col_kernel(const float* __restrict__ acc, T* __restrict__ out, int cout) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= cout * 32) return;
-  const int o = i / 32, k = i % 32;
-  float v = 0.f;
-  if (k < 27) { const int t = k / 3, c = k % 3; v = acc[(o * 3 + c) * 9 + t]; }
-  out[i] = Elem<T>::from_f(v);
-}
-// identity matrix [n][n] (K-major rows) in the activation dtype: the residual of a 3x3 conv rides the GEMM as one more K-slab
-template <typename T>
-__global__ void identity_store_kernel(T* __restrict__ out, int n) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= static_cast<long long>(n) * n) return;
-  out[i] = Elem<T>::from_f((i / n) == (i % n) ? 1.f : 0.f);
-}
-static __global__ void bias_store_kernel(const float* __restrict__ b, float* __restrict__ out, int cout, int row_off,
-                                  int interleave_half, const float* __restrict__ add) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= cout) return;
-  int orow = o;
-  if (interleave_half > 0) orow = (o < interleave_half) ? 2 * o : 2 * (o - interleave_half) + 1;
-  out[orow + row_off] = (b ? b[o] : 0.f) + (add ? add[o] : 0.f);
-}
-// y = act(W x + b), W [out][in] fp32, one warp per output (time-embedding MLP, computed once: t == 999)
-static __global__ void gemv_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ x,
-                            float* __restrict__ y, int out, int in, int silu_out) {
-  const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (o >= out) return;
-  float a = 0.f;
-  for (int i = lane; i < in; i += 32) a += W[static_cast<long long>(o) * in + i] * x[i];
-  a = warp_sum(a);
-  if (lane == 0) {
-    a += b ? b[o] : 0.f;
-    y[o] = silu_out ? silu_f(a) : a;
-  }
-}
-// acc[o][j] (Linear weight, fp32) fold helper for gemv inputs: reuse wprep_init/wprep_lora on a scratch copy.
 
 }  // namespace i2it

@@ -50,7 +50,7 @@ Act Engine::vae_attn(Plan& P, const std::string& p, const Act& x) {
   return linear(P, a, prep(p + ".to_out.0", {p + ".to_out.0"}), &x);
 }
 
-Act Engine::build_vae_encoder(Plan& P, const std::string& vp, int B, int H, int W, std::vector<Act>& skips) {
+Act Engine::build_vae_encoder(Plan& P, const std::string& vp, int B, int H, int W, std::vector<Act>& skips, bool u8_in) {
   const std::string e = vp + "encoder";
   // conv_in (3 -> C0, 3x3): the NCHW boundary tensor is packed straight into im2col rows [B,H,W,32] (27 taps*channels + 5
   // zeros), so the conv is ONE K=32 GEMM tap with 64-byte TMA rows instead of nine taps of 16-byte rows
@@ -60,10 +60,17 @@ Act Engine::build_vae_encoder(Plan& P, const std::string& vp, int B, int H, int 
     uint16_t* yp = xcol.p;
     Plan* plan = &P;
     const int dt = dtype, hh = H, ww = W;
-    add_op(P, [=](cudaStream_t st) {
-      DISPATCH_T(dt, (launch_k(pack_input_im2col_kernel<T>, dim3(ceil_div_i(total, 128)), dim3(128), 0, st, 0,
-                         reinterpret_cast<const T*>(plan->io.x), reinterpret_cast<T*>(yp), hh, ww, total)));
-    }, "pack_im2col", 0, 2.0 * total * (3 + 32));
+    if (u8_in) {
+      add_op(P, [=](cudaStream_t st) {
+        DISPATCH_T(dt, (launch_k(pack_input_im2col_u8_kernel<T>, dim3(ceil_div_i(total, 128)), dim3(128), 0, st, 0,
+                           reinterpret_cast<const uint8_t*>(plan->io.x_u8), reinterpret_cast<T*>(yp), hh, ww, total, plan->io.in_mode)));
+      }, "pack_im2col_u8", 0, 1.0 * total * (3 + 64));
+    } else {
+      add_op(P, [=](cudaStream_t st) {
+        DISPATCH_T(dt, (launch_k(pack_input_im2col_kernel<T>, dim3(ceil_div_i(total, 128)), dim3(128), 0, st, 0,
+                           reinterpret_cast<const T*>(plan->io.x), reinterpret_cast<T*>(yp), hh, ww, total)));
+      }, "pack_im2col", 0, 2.0 * total * (3 + 32));
+    }
   }
   ConvOpts oin; oin.ksize = 1;
   Act s = conv(P, xcol, prep_im2col3(e + ".conv_in"), oin);
@@ -136,6 +143,10 @@ void Engine::build_vae_decoder(Plan& P, const std::string& vp, const Act& dec_in
     mark(P, "dec_up" + std::to_string(i), s);
   }
   s = group_norm(P, s, norm(d + ".conv_norm_out"), 1e-6f, true);
+  if (cfg.keep_stages) {   // tests compare the PRE-clamp image: one extra launch, test mode only
+    Act pre = conv(P, s, prep(d + ".conv_out", {d + ".conv_out"}), ConvOpts());
+    mark(P, "pre_clamp", pre);
+  }
   ConvOpts oo; oo.act = TG_ACT_CLAMP1; oo.to_io_out_nchw = true;
   conv(P, s, prep(d + ".conv_out", {d + ".conv_out"}), oo);
 }
@@ -173,8 +184,15 @@ Act Engine::unet_xformer(Plan& P, const std::string& p, const Act& x, int heads,
   {  // cross-attention over the 77 text tokens
     Act n = layer_norm(P, t, norm(b + ".norm2"));
     Act q = linear(P, n, prep(b + ".attn2.to_q", {b + ".attn2.to_q"}));
-    Act k2 = linear(P, text_, prep(b + ".attn2.to_k", {b + ".attn2.to_k"}));
-    Act v2t = vt_proj(P, text_, text_batch, 77, prep(b + ".attn2.to_v", {b + ".attn2.to_v"}));
+    Act k2, v2t;
+    if (text_kv_) {                                   // computed once per prompt by i2it_set_text
+      auto it = text_kv_->kv.find(b);
+      I2IT_CHECK(it != text_kv_->kv.end(), "no cached text K/V for " + b);
+      k2 = it->second.first; v2t = it->second.second;
+    } else {
+      k2 = linear(P, text_, prep(b + ".attn2.to_k", {b + ".attn2.to_k"}));
+      v2t = vt_proj(P, text_, text_batch, 77, prep(b + ".attn2.to_v", {b + ".attn2.to_v"}));
+    }
     Act a = attention(P, q, k2, v2t, B, N, 77, heads, d, text_batch);
     a.N = x.N; a.H = x.H; a.W = x.W;
     t = linear(P, a, prep(b + ".attn2.to_out.0", {b + ".attn2.to_out.0"}), &t);
@@ -187,14 +205,54 @@ Act Engine::unet_xformer(Plan& P, const std::string& p, const Act& x, int heads,
   return linear(P, t, prep(p + ".proj_out", {p + ".proj_out"}), &x);
 }
 
-Act Engine::build_unet(Plan& P, const Act& z, int text_batch) {
+// every transformer block of the UNet, in execution-independent fixed order (the cross-attention K/V^T cache is keyed by it)
+std::vector<std::string> Engine::xformer_prefixes() const {
+  std::vector<std::string> v;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 2; ++j) v.push_back("unet.down_blocks." + std::to_string(i) + ".attentions." + std::to_string(j));
+  v.push_back("unet.mid_block.attentions.0");
+  for (int i = 1; i < 4; ++i)
+    for (int j = 0; j < 3; ++j) v.push_back("unet.up_blocks." + std::to_string(i) + ".attentions." + std::to_string(j));
+  return v;
+}
+
+// K = to_k(text), V^T = (to_v(text))^T of every cross-attention layer: 2 launches per block, run only when the prompt changes
+void Engine::build_text_kv(TextKV& T) {
+  Plan& P = T.plan;
+  T.text = alloc_act(P, T.text_batch, 1, 77, cfg.cross_dim);
+  {
+    uint16_t* tp = T.text.p;
+    const size_t bytes = static_cast<size_t>(T.text_batch) * 77 * cfg.cross_dim * 2;
+    Plan* plan = &P;
+    add_op(P, [=](cudaStream_t st) {
+      cudaMemcpyAsync(tp, plan->io.text, bytes, cudaMemcpyDeviceToDevice, st);
+      g_pdl.prev_is_kernel = false;
+    });
+  }
+  for (const auto& p : xformer_prefixes()) {
+    const std::string b = p + ".transformer_blocks.0";
+    Act k2 = linear(P, T.text, prep(b + ".attn2.to_k", {b + ".attn2.to_k"}));
+    Act v2t = vt_proj(P, T.text, T.text_batch, 77, prep(b + ".attn2.to_v", {b + ".attn2.to_v"}));
+    T.kv[b] = std::make_pair(k2, v2t);
+  }
+  flush_prep();
+  I2IT_CUDA(cudaDeviceSynchronize());
+}
+
+Act Engine::build_unet(Plan& P, const Act& z, int text_batch, bool text_cached) {
   const std::string u = "unet";
   const int* ch = cfg.unet_channels;
   const int* heads = cfg.unet_heads;
-  // stage the text embedding: its projections are TMA operands, whose maps need a fixed base address
-  text_ = alloc_act(P, text_batch, 1, 77, cfg.cross_dim);
-  P.keep.push_back(text_.hold);
-  {
+  text_kv_ = nullptr;
+  if (text_cached) {
+    auto it = textkv_.find(text_batch);
+    I2IT_CHECK(it != textkv_.end(), "text_emb == NULL but i2it_set_text has not been called for this text_batch since the last "
+                                    "i2it_finalize_weights");
+    text_kv_ = it->second.get();
+  } else {
+    // stage the text embedding: its projections are TMA operands, whose maps need a fixed base address
+    text_ = alloc_act(P, text_batch, 1, 77, cfg.cross_dim);
+    P.keep.push_back(text_.hold);
     uint16_t* tp = text_.p;
     const size_t bytes = static_cast<size_t>(text_batch) * 77 * cfg.cross_dim * 2;
     Plan* plan = &P;
@@ -250,12 +308,13 @@ Act Engine::build_unet(Plan& P, const Act& z, int text_batch) {
   s = group_norm(P, s, norm(u + ".conv_norm_out"), 1e-5f, true);
   s = conv(P, s, prep(u + ".conv_out", {u + ".conv_out"}), ConvOpts());
   text_ = Act();
+  text_kv_ = nullptr;
   return s;
 }
 
 // ------------------------------------------------------------------------------------------ whole path
-Plan* Engine::plan_for(int B, int H, int W, int direction, int text_batch) {
-  const std::vector<int> key{B, H, W, direction, text_batch};
+Plan* Engine::plan_for(int B, int H, int W, int direction, int text_batch, bool text_cached, int io_mode) {
+  const std::vector<int> key{B, H, W, direction, text_batch, text_cached ? 1 : 0, io_mode};
   auto it = plans_.find(key);
   if (it != plans_.end()) return it->second.get();
   I2IT_CHECK(finalized_, "i2it_finalize_weights must be called before a forward");
@@ -263,10 +322,20 @@ Plan* Engine::plan_for(int B, int H, int W, int direction, int text_batch) {
   if (cfg.model_kind == I2IT_CYCLEGAN && direction == I2IT_B2A) vp = "vae_b2a.";
   std::unique_ptr<Plan> up(new Plan());
   Plan& P = *up;
+  P.key = key;
   std::vector<Act> skips;
-  Act z = build_vae_encoder(P, vp, B, H, W, skips);
-  Act pred = build_unet(P, z, text_batch);
+  if (io_mode & IO_U8_OUT) {
+    // allocated FIRST and held for the plan's lifetime: pool liveness follows build order, and the last conv writes here
+    auto tmp = alloc_raw(P, static_cast<size_t>(B) * 3 * H * W * 2);
+    P.keep.push_back(tmp);
+    P.u8_out_tmp = tmp.get();
+  }
+  P.ranges.emplace_back(P.ops.size(), "vae_encode");
+  Act z = build_vae_encoder(P, vp, B, H, W, skips, (io_mode & IO_U8_IN) != 0);
+  P.ranges.emplace_back(P.ops.size(), "unet");
+  Act pred = build_unet(P, z, text_batch, text_cached);
   mark(P, "model_pred", pred);
+  P.ranges.emplace_back(P.ops.size(), "ddpm_step");
   Act dec_in = alloc_act(P, B, H / 8, W / 8, 8, 8, true);
   {
     // alpha_bar_999 of the scaled-linear schedule (fp32 cumprod, as diffusers computes it): 0.0046600951
@@ -276,17 +345,31 @@ Plan* Engine::plan_for(int B, int H, int W, int direction, int text_batch) {
     const uint16_t* pp = pred.p;
     uint16_t* dp = dec_in.p;
     const int ldp = pred.ld, dt = dtype;
+    // the two wrappers call DDPMScheduler.step with different timestep shapes => different rounding (kernels.cuh)
+    const int three_round = (cfg.model_kind == I2IT_CYCLEGAN) ? 1 : 0;
     Plan* plan = &P;
     P.keep.push_back(z.hold);
     P.keep.push_back(pred.hold);
     add_op(P, [=](cudaStream_t st) {
       DISPATCH_T(dt, (launch_k(ddpm_step_kernel<T>, dim3(ceil_div_i(total, 128)), dim3(128), 0, st, 0,
                          reinterpret_cast<const T*>(zp), reinterpret_cast<const T*>(pp), ldp, s1, sa, inv_sf,
-                         reinterpret_cast<T*>(dp), reinterpret_cast<T*>(plan->io.out_latent), HW, total)));
+                         reinterpret_cast<T*>(dp), reinterpret_cast<T*>(plan->io.out_latent), HW, total, three_round)));
     });
   }
   mark(P, "dec_in", dec_in);
+  P.ranges.emplace_back(P.ops.size(), "vae_decode");
   build_vae_decoder(P, vp, dec_in, skips);
+  if (io_mode & IO_U8_OUT) {
+    // the last conv wrote NCHW into an internal buffer (forward() points io.out at it); convert to uint8 HWC for the caller
+    const long long HW = static_cast<long long>(H) * W, total = HW * B;
+    const int dt = dtype;
+    Plan* plan = &P;
+    add_op(P, [=](cudaStream_t st) {
+      DISPATCH_T(dt, (launch_k(nchw_to_u8hwc_kernel<T>, dim3(ceil_div_i(total, 256)), dim3(256), 0, st, 0,
+                         reinterpret_cast<const T*>(plan->io.out), reinterpret_cast<uint8_t*>(plan->io.out_u8), HW, total)));
+    }, "unpack_u8", 0, 1.0 * total * (6 + 3));
+  }
+  flush_prep();                             // every weight of the plan: one fold/re-layout launch (+ the time-embedding GEMVs)
   I2IT_CUDA(cudaDeviceSynchronize());       // weight preparation ran on the default stream
   I2IT_CUDA(cudaGetLastError());
   Plan* raw_plan = up.get();

@@ -59,7 +59,8 @@ class CycleGAN_Turbo(TurboBase):
 
     def __init__(self, pretrained_name=None, pretrained_path=None, ckpt_folder="checkpoints", lora_rank_unet=8,
                  lora_rank_vae=4, *, cfg=None, seed=0, lora_b_std=0.02, perturb_norm=False, text_stack=None,
-                 use_cuda_graph=True, keep_stages=False, synthetic_caption=None, synthetic_direction=None):
+                 use_cuda_graph=True, keep_stages=False, synthetic_caption=None, synthetic_direction=None,
+                 allow_synthetic_weights=False):
         super().__init__()
         self._init_common(cfg, None, text_stack, use_cuda_graph, keep_stages)
         ckpt = None
@@ -73,8 +74,15 @@ class CycleGAN_Turbo(TurboBase):
             try:
                 download_url(url, outf)
                 ckpt = torch.load(outf, map_location="cpu")
-            except Exception as ex:   # offline: keep caption/direction of the named model, weights stay synthetic
-                warnings.warn(f"checkpoint {url} unreachable ({type(ex).__name__}); using seeded random weights")
+            except Exception as ex:
+                # A named pretrained model on random weights produces garbage images: refuse unless explicitly asked for
+                # (offline synthetic benchmarks pass allow_synthetic_weights=True and keep the caption/direction).
+                if not allow_synthetic_weights:
+                    raise RuntimeError(f"could not load the {pretrained_name!r} checkpoint from {url} ({type(ex).__name__}: {ex}); "
+                                       "pass allow_synthetic_weights=True to run the named configuration on seeded random "
+                                       "weights (benchmarks only)") from ex
+                warnings.warn(f"checkpoint {url} unreachable ({type(ex).__name__}); using seeded random weights "
+                              "(allow_synthetic_weights=True)")
         elif pretrained_path is not None:
             ckpt = torch.load(pretrained_path, map_location="cpu")
         else:
@@ -102,6 +110,10 @@ class CycleGAN_Turbo(TurboBase):
 
     # ---- checkpoint format written by train_cyclegan_turbo.py:293-307, read at cyclegan_turbo.py:162-190 ----
     def load_ckpt_from_state_dict(self, sd):
+        # adapters exist only where the checkpoint has them (reference :163-183 builds the LoraConfigs from the checkpoint's
+        # target lists): drop the seeded ones first so no layer keeps a random, never-trained adapter
+        for k in [k for k in self._sd if ".lora_A." in k or ".lora_B." in k]:
+            del self._sd[k]
         for part, adapter in (("sd_encoder", "default_encoder"), ("sd_decoder", "default_decoder"), ("sd_other", "default_others")):
             for k, v in sd[part].items():
                 k2 = k.replace(".lora_A.weight", f".lora_A.{adapter}.weight").replace(".lora_B.weight", f".lora_B.{adapter}.weight")
@@ -163,3 +175,24 @@ class CycleGAN_Turbo(TurboBase):
             caption_enc = self._encode_text(caption)
         return self.forward_with_networks(x_t, direction, self.vae_enc, self.unet, self.vae_dec, self.sched, self.timesteps,
                                           caption_enc, eps)
+
+    def forward_u8(self, images_u8, direction=None, caption=None, caption_emb=None, *, eps=None):
+        """uint8 HWC boundary: [B,H,W,3] uint8 -> [B,H,W,3] uint8 CUDA tensor.  Fuses ToTensor + Normalize([0.5],[0.5])
+        (inference_unpaired.py:45-47) and ToPILImage()(out*0.5+0.5) (:53) around the same fused forward."""
+        if direction is None:
+            assert self.direction is not None
+            direction = self.direction
+        if caption is None and caption_emb is None:
+            assert self.caption is not None
+            caption = self.caption
+        assert direction in ["a2b", "b2a"]
+        dt = self.compute_dtype
+        text = self._prep(caption_emb if caption_emb is not None else self._encode_text(caption), dt)
+        x = images_u8.to(device="cuda", non_blocking=True).contiguous()
+        B, H, Wd, _ = x.shape
+        if eps is None:
+            eps = torch.randn((B, 4, H // 8, Wd // 8), device="cuda", dtype=dt)
+        eps = self._prep(eps, dt)
+        eng = self._finalize(1.0, 1.0, 1.0, -1.0)
+        return self._staged_forward(eng, x, text, eps, direction=i2it.A2B if direction == "a2b" else i2it.B2A,
+                                    u8_mode=i2it.IN_NORMALIZE)

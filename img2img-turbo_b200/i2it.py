@@ -19,6 +19,7 @@ F16, BF16, F32 = 0, 1, 2
 PIX2PIX, CYCLEGAN = 0, 1
 A2B, B2A = 0, 1
 ACT_NONE, ACT_CLAMP1, ACT_GEGLU = 0, 1, 2
+IN_UNIT, IN_NORMALIZE, IN_SKETCH = 0, 1, 2      # uint8 input transforms of i2it_forward_u8
 
 _TORCH2DT = {torch.float16: F16, torch.bfloat16: BF16, torch.float32: F32}
 _DT2TORCH = {F16: torch.float16, BF16: torch.bfloat16}
@@ -27,7 +28,7 @@ _DT2TORCH = {F16: torch.float16, BF16: torch.bfloat16}
 SYMBOLS = [
     "i2it_default_config", "i2it_create", "i2it_destroy", "i2it_last_error", "i2it_set_weight",
     "i2it_set_adapter_scale", "i2it_finalize_weights", "i2it_workspace_bytes", "i2it_forward",
-    "i2it_launch_count", "i2it_profile", "i2it_read_stage", "i2it_op_conv2d", "i2it_op_group_norm", "i2it_op_layer_norm",
+    "i2it_set_text", "i2it_forward_u8", "i2it_prep_launch_count", "i2it_launch_count", "i2it_profile", "i2it_read_stage", "i2it_op_conv2d", "i2it_op_group_norm", "i2it_op_layer_norm",
     "i2it_op_attention", "i2it_op_upsample2x",
 ]
 
@@ -67,6 +68,9 @@ def load_library(path: Optional[str] = None):
     lib.i2it_finalize_weights.argtypes = [vp, cf, cf, cf, cf]
     lib.i2it_workspace_bytes.argtypes = [vp, ci, ci, ci, C.POINTER(C.c_size_t)]
     lib.i2it_forward.argtypes = [vp, vp, vp, ci, vp, vp, cf, vp, vp, ci, ci, ci, ci, vp]
+    lib.i2it_set_text.argtypes = [vp, vp, ci, vp]
+    lib.i2it_forward_u8.argtypes = [vp, vp, ci, vp, ci, vp, vp, cf, vp, vp, ci, ci, ci, ci, vp]
+    lib.i2it_prep_launch_count.argtypes = [vp, C.POINTER(ci)]
     lib.i2it_launch_count.argtypes = [vp, ci, ci, ci, ci, C.POINTER(ci)]
     lib.i2it_profile.argtypes = [vp, ci, C.c_char_p, C.c_size_t, vp]
     lib.i2it_read_stage.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(ci)]
@@ -153,29 +157,69 @@ class Engine:
 
     def finalize(self, lora_weight_unet: float = 1.0, lora_weight_vae: float = 1.0, skip_gamma: float = 1.0,
                  twin_r: float = -1.0):
+        self._text_batch = None          # cached text projections die with the folded weights
         self._check(self.lib.i2it_finalize_weights(self._h, lora_weight_unet, lora_weight_vae, skip_gamma, twin_r),
                     "i2it_finalize_weights")
 
     # ---- the hot path ----------------------------------------------------------------------------
-    def forward(self, x: torch.Tensor, text_emb: torch.Tensor, eps: torch.Tensor,
+    def set_text(self, text_emb: torch.Tensor):
+        """Cache the cross-attention K / V^T of a prompt embedding [1|B,77,cross]; later forwards pass text_emb=None."""
+        if not (text_emb.is_cuda and text_emb.is_contiguous() and text_emb.dtype == self.dtype):
+            raise ValueError("libi2it operands must be contiguous CUDA tensors in the engine dtype")
+        if text_emb.dim() != 3 or text_emb.shape[1:] != (77, self.cross_dim):
+            raise ValueError(f"text_emb must be [1|B,77,{self.cross_dim}]")
+        self._check(self.lib.i2it_set_text(self._h, _ptr(text_emb), text_emb.shape[0], _stream()), "i2it_set_text")
+        self._text_batch = text_emb.shape[0]
+
+    def _check_operands(self, B, H, W, text_emb, eps, others):
+        for t in (text_emb, eps) + tuple(others):
+            if t is not None:
+                if not (t.is_cuda and t.is_contiguous() and t.dtype == self.dtype):
+                    raise ValueError("libi2it operands must be contiguous CUDA tensors in the engine dtype")
+        if text_emb is not None:
+            if text_emb.shape[1:] != (77, self.cross_dim) or text_emb.shape[0] not in (1, B):
+                raise ValueError(f"text_emb must be [1|B,77,{self.cross_dim}]")
+            tb = text_emb.shape[0]
+        else:
+            tb = getattr(self, "_text_batch", None)
+            if tb is None:
+                raise ValueError("text_emb=None needs a previous set_text()")
+        if eps.shape != (B, 4, H // 8, W // 8):
+            raise ValueError("eps must be [B,4,H/8,W/8]")
+        return tb
+
+    def forward(self, x: torch.Tensor, text_emb: Optional[torch.Tensor], eps: torch.Tensor,
                 noise_map: Optional[torch.Tensor] = None, r: float = 1.0, direction: int = A2B,
                 out: Optional[torch.Tensor] = None, out_latent: Optional[torch.Tensor] = None) -> torch.Tensor:
         B, Cc, H, W = x.shape
         assert Cc == 3, "image must be [B,3,H,W]"
-        for t in (x, text_emb, eps, noise_map, out, out_latent):
-            if t is not None:
-                if not (t.is_cuda and t.is_contiguous() and t.dtype == self.dtype):
-                    raise ValueError("libi2it operands must be contiguous CUDA tensors in the engine dtype")
-        if text_emb.shape[1:] != (77, self.cross_dim) or text_emb.shape[0] not in (1, B):
-            raise ValueError(f"text_emb must be [1|B,77,{self.cross_dim}]")
-        if eps.shape != (B, 4, H // 8, W // 8):
-            raise ValueError("eps must be [B,4,H/8,W/8]")
+        tb = self._check_operands(B, H, W, text_emb, eps, (x, noise_map, out, out_latent))
         if out is None:
             out = torch.empty_like(x)
-        self._check(self.lib.i2it_forward(self._h, _ptr(x), _ptr(text_emb), text_emb.shape[0], _ptr(eps), _ptr(noise_map),
+        self._check(self.lib.i2it_forward(self._h, _ptr(x), _ptr(text_emb), tb, _ptr(eps), _ptr(noise_map),
                                           float(r), _ptr(out), _ptr(out_latent), B, H, W, direction, _stream()),
                     "i2it_forward")
         return out
+
+    def forward_u8(self, x_u8: torch.Tensor, in_mode: int, text_emb: Optional[torch.Tensor], eps: torch.Tensor,
+                   noise_map: Optional[torch.Tensor] = None, r: float = 1.0, direction: int = A2B,
+                   out: Optional[torch.Tensor] = None, out_latent: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """uint8 HWC boundary: x_u8 [B,H,W,3] uint8 CUDA -> [B,H,W,3] uint8 CUDA (pre/post-processing fused on device)."""
+        B, H, W, Cc = x_u8.shape
+        assert Cc == 3 and x_u8.dtype == torch.uint8 and x_u8.is_cuda and x_u8.is_contiguous(), "image must be uint8 CUDA [B,H,W,3]"
+        tb = self._check_operands(B, H, W, text_emb, eps, (noise_map, out_latent))
+        if out is None:
+            out = torch.empty_like(x_u8)
+        assert out.dtype == torch.uint8 and out.is_cuda and out.is_contiguous() and out.shape == x_u8.shape
+        self._check(self.lib.i2it_forward_u8(self._h, _ptr(x_u8), int(in_mode), _ptr(text_emb), tb, _ptr(eps), _ptr(noise_map),
+                                             float(r), _ptr(out), _ptr(out_latent), B, H, W, direction, _stream()),
+                    "i2it_forward_u8")
+        return out
+
+    def prep_launch_count(self) -> int:
+        n = C.c_int(0)
+        self._check(self.lib.i2it_prep_launch_count(self._h, C.byref(n)), "i2it_prep_launch_count")
+        return n.value
 
     def launch_count(self, B: int, H: int, W: int, direction: int = A2B) -> int:
         n = C.c_int(0)

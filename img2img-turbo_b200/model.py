@@ -30,7 +30,9 @@ def download_url(url, outf):
     print(f"Downloading checkpoint to {outf}")
     response = requests.get(url, stream=True)
     response.raise_for_status()
-    with open(outf, "wb") as f:
+    tmp = outf + ".part"                      # an interrupted download must never be mistaken for the checkpoint
+    with open(tmp, "wb") as f:
         for chunk in response.iter_content(1 << 20):
             f.write(chunk)
+    os.replace(tmp, outf)
     print(f"Downloaded successfully to {outf}")

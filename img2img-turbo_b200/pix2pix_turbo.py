@@ -54,10 +54,12 @@ class Pix2Pix_Turbo(TurboBase):
 
     def __init__(self, pretrained_name=None, pretrained_path=None, ckpt_folder="checkpoints", lora_rank_unet=8,
                  lora_rank_vae=4, *, cfg=None, seed=0, lora_b_std=0.02, perturb_norm=False, text_stack=None,
-                 use_cuda_graph=True, keep_stages=False):
+                 use_cuda_graph=True, keep_stages=False, twin=False):
         super().__init__()
         self._init_common(cfg, None, text_stack, use_cuda_graph, keep_stages)
-        twin = pretrained_name == "sketch_to_image_stochastic"
+        # twin=True: random-init model WITH a TwinConv conv_in (two distinct weight sets) — the synthetic stand-in for the
+        # sketch_to_image_stochastic checkpoint (BASELINE config #4)
+        twin = bool(twin) or pretrained_name == "sketch_to_image_stochastic"
         ckpt = None
         if pretrained_name in CKPT_URLS:
             os.makedirs(ckpt_folder, exist_ok=True)
@@ -97,15 +99,42 @@ class Pix2Pix_Turbo(TurboBase):
 
     # ---- checkpoint format of save_model (reference pix2pix_turbo.py:221-229, read at :66-78) ----
     def _apply_checkpoint(self, ckpt):
+        """The reference creates adapters ONLY for the checkpoint's target modules (LoraConfig(target_modules=sd[...]),
+        pix2pix_turbo.py:66-78) and then overlays the checkpoint tensors.  So: drop every adapter of the seeded base, overlay,
+        and check that each layer the checkpoint's target lists name got its LoRA pair."""
+        for k in [k for k in self._sd if ".lora_A." in k or ".lora_B." in k]:
+            del self._sd[k]
         for part, prefix in (("state_dict_unet", "unet."), ("state_dict_vae", "vae.")):
             for k, v in ckpt[part].items():
                 self._sd[prefix + k.replace(".base_layer.", ".")] = v.detach().float().cpu()
+        for prefix, targets, adapter in (("unet.", ckpt.get("unet_lora_target_modules"), "default"),
+                                         ("vae.", ckpt.get("vae_lora_target_modules"), "vae_skip")):
+            if not targets:
+                continue
+            layers = {k[:-len(".weight")] for k in self._sd if k.startswith(prefix) and k.endswith(".weight") and ".lora_" not in k
+                      and self._sd[k].dim() in (2, 4)}
+            missing = [l for l in sorted(layers) if W._suffix_match(l[len(prefix):], list(targets))
+                       and f"{l}.lora_A.{adapter}.weight" not in self._sd]
+            if missing:
+                warnings.warn(f"checkpoint lists {len(missing)} {prefix[:-1]} LoRA target layers without LoRA tensors (e.g. "
+                              f"{missing[0]}): they run without an adapter (the reference would initialise lora_B = 0, a no-op)")
+
+    @staticmethod
+    def _peft_keys(sd):
+        """State dict in peft's spelling: the base weight/bias of every LoRA-wrapped layer is `X.base_layer.weight`
+        (what the reference's strict load_state_dict expects, pix2pix_turbo.py:66-78,111-125)."""
+        wrapped = {k.split(".lora_A.")[0] for k in sd if ".lora_A." in k}
+        out = {}
+        for k, v in sd.items():
+            stem, _, leaf = k.rpartition(".")
+            out[f"{stem}.base_layer.{leaf}" if (stem in wrapped and leaf in ("weight", "bias")) else k] = v
+        return out
 
     def save_model(self, outf):
         sd = {"unet_lora_target_modules": self.target_modules_unet, "vae_lora_target_modules": self.target_modules_vae,
               "rank_unet": self.lora_rank_unet, "rank_vae": self.lora_rank_vae,
-              "state_dict_unet": {k: v for k, v in self.unet.state_dict().items() if "lora" in k or "conv_in" in k},
-              "state_dict_vae": {k: v for k, v in self.vae.state_dict().items() if "lora" in k or "skip" in k}}
+              "state_dict_unet": {k: v for k, v in self._peft_keys(self.unet.state_dict()).items() if "lora" in k or "conv_in" in k},
+              "state_dict_vae": {k: v for k, v in self._peft_keys(self.vae.state_dict()).items() if "lora" in k or "skip" in k}}
         torch.save(sd, outf)
 
     def set_eval(self):
@@ -160,3 +189,34 @@ class Pix2Pix_Turbo(TurboBase):
             if self._twin:
                 self.unet.conv_in.r = None
         return out if in_dtype == dt else out.to(in_dtype)
+
+    def forward_u8(self, images_u8, prompt=None, prompt_tokens=None, deterministic=True, r=1.0, noise_map=None, *, eps=None,
+                   sketch=False):
+        """uint8 HWC boundary: `images_u8` [B,H,W,3] uint8 (host or device) -> [B,H,W,3] uint8 CUDA tensor.
+        Fuses F.to_tensor (edge/canny images, inference_paired.py:50) or the sketch threshold (:56-57) on the way in and
+        ToPILImage()(out*0.5+0.5) (:72) on the way out; everything between is the same i2it_forward."""
+        assert (prompt is None) != (prompt_tokens is None), "Either prompt or prompt_tokens should be provided"
+        dt = self.compute_dtype
+        caption_enc = self._encode_text(prompt, prompt_tokens)
+        x = images_u8.to(device="cuda", non_blocking=True).contiguous()
+        B, H, Wd, _ = x.shape
+        if eps is None:
+            eps = torch.randn((B, 4, H // 8, Wd // 8), device="cuda", dtype=dt)
+            torch.randn((B, 4, H // 8, Wd // 8), device="cuda", dtype=dt)
+        eps = self._prep(eps, dt)
+        mode = i2it.IN_SKETCH if sketch else i2it.IN_UNIT
+        if deterministic:
+            if self._twin:
+                raise TypeError("deterministic forward on a TwinConv model: conv_in.r is None (as in the reference)")
+            eng = self._finalize(self._lora_w_unet, self._lora_w_vae, float(self.vae.decoder.gamma), -1.0)
+            return self._staged_forward(eng, x, caption_enc, eps, u8_mode=mode)
+        if noise_map is None:
+            raise ValueError("noise_map is required when deterministic=False")
+        self._lora_w_unet = self._lora_w_vae = float(r)
+        self.vae.decoder.gamma = r
+        eng = self._finalize(r, r, r, r if self._twin else -1.0)
+        nm = self._prep(noise_map.expand(B, -1, -1, -1) if noise_map.shape[0] != B else noise_map, dt)
+        out = self._staged_forward(eng, x, caption_enc, eps, noise=nm, r=float(r), u8_mode=mode)
+        if self._twin:
+            self.unet.conv_in.r = None
+        return out

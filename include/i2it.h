@@ -34,6 +34,10 @@ typedef struct i2it_handle i2it_handle;
 enum { I2IT_F16 = 0, I2IT_BF16 = 1, I2IT_F32 = 2 };
 enum { I2IT_PIX2PIX = 0, I2IT_CYCLEGAN = 1 };
 enum { I2IT_A2B = 0, I2IT_B2A = 1 };
+/* uint8 input transforms of i2it_forward_u8 (what the reference CLIs do on the host before the forward) */
+enum { I2IT_IN_UNIT = 0,        /* F.to_tensor(img): u8/255                       src/inference_paired.py:50      */
+       I2IT_IN_NORMALIZE = 1,   /* ToTensor + Normalize([0.5],[0.5])              src/inference_unpaired.py:45-47 */
+       I2IT_IN_SKETCH = 2 };    /* (F.to_tensor(img) < 0.5).float()               src/inference_paired.py:56-57   */
 
 /* Network hyper-parameters (HF config.json of stabilityai/sd-turbo; i2it_default_config fills them in). */
 typedef struct i2it_config {
@@ -92,13 +96,38 @@ int i2it_workspace_bytes(i2it_handle* h, int batch, int H, int W, size_t* bytes)
  *   out      [batch, 3, H, W]          clamp(-1,1) image
  *   out_latent [batch, 4, H/8, W/8]    nullable; x_denoised (the "output latents")
  * direction selects vae (A2B) or vae_b2a (B2A) for I2IT_CYCLEGAN; ignored for I2IT_PIX2PIX.
+ * text_emb may be NULL: the cross-attention K / V^T cached by the last i2it_set_text(…, text_batch) are used (one prompt,
+ * many images: the reference re-projects the 77 text tokens in all 16 cross-attention layers on every forward).
+ * The DDPM step follows the wrapper the handle was created for: fp32 with one rounding for I2IT_PIX2PIX
+ * (src/pix2pix_turbo.py:162,200-201: 1-D timesteps), three activation-dtype roundings for I2IT_CYCLEGAN
+ * (src/cyclegan_turbo.py:205: 0-dim timestep).
  * H and W must be multiples of 64.  `stream` is a cudaStream_t. */
 int i2it_forward(i2it_handle* h, const void* x, const void* text_emb, int text_batch, const void* eps,
                  const void* noise_map, float r, void* out, void* out_latent, int batch, int H, int W,
                  int direction, void* stream);
 
-/* Number of kernel launches one forward of this shape issues (for bench accounting). */
+/* Project and cache the cross-attention operands of a prompt: K = to_k(text_emb), V^T = to_v(text_emb)^T for every
+ * transformer block (32 small launches, enqueued on `stream`).  text_emb [text_batch, 77, cross] device pointer in the
+ * handle dtype; it is consumed before the call returns control to the stream order (the caller may reuse the buffer after
+ * the stream reaches this point).  Must be called again after i2it_finalize_weights (the projections carry the LoRA scale).
+ * Replaces the per-forward `attn2.to_k / attn2.to_v` calls under unet(...) at /root/reference/src/pix2pix_turbo.py:199. */
+int i2it_set_text(i2it_handle* h, const void* text_emb, int text_batch, void* stream);
+
+/* i2it_forward with a uint8 HWC boundary: x_u8_hwc [batch, H, W, 3] and out_u8_hwc [batch, H, W, 3] are device pointers.
+ * Input transform `in_mode` (I2IT_IN_*) and the output `ToPILImage()(out*0.5+0.5)` (src/inference_paired.py:72,
+ * src/inference_unpaired.py:53; three activation-dtype roundings then truncation to uint8) are fused into the first /
+ * a trailing kernel, so a caller moves 3 bytes per pixel each way instead of 2 x 3 x sizeof(half). */
+int i2it_forward_u8(i2it_handle* h, const void* x_u8_hwc, int in_mode, const void* text_emb, int text_batch,
+                    const void* eps, const void* noise_map, float r, void* out_u8_hwc, void* out_latent, int batch,
+                    int H, int W, int direction, void* stream);
+
+/* Number of kernel launches one forward of this shape issues (for bench accounting): the plan the last forward used if it
+ * has this shape, else the plan with the text embedding passed inline. */
 int i2it_launch_count(i2it_handle* h, int batch, int H, int W, int direction, int* launches);
+
+/* Kernel launches spent on weight preparation (LoRA fold / TwinConv / re-layout / time embedding) since the handle was
+ * created: a job table makes this 4-5 per finalize+plan instead of one to four per tensor. */
+int i2it_prep_launch_count(i2it_handle* h, int* launches);
 
 /* Per-launch device timing of the plan the LAST forward used: runs it `reps` more times with CUDA events around
  * every launch and writes a JSON array [{"i","kind","ms","flops","bytes","shape"}...] (algorithmic flops/bytes per
