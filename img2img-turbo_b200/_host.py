@@ -18,6 +18,12 @@ import i2it
 import weights as W
 
 SD_TURBO_DIR_ENV = "I2IT_SD_TURBO_DIR"      # optional local snapshot of stabilityai/sd-turbo (offline boxes)
+DEVICE = "cuda"      # where the wrappers stage tensors.  tests/cpu_stub_engine.py (a TEST DOUBLE of i2it.Engine used to run the
+                     # unmodified reference CLIs on GPU-less hosts) sets this to "cpu"; the product never does.
+
+
+def _cur_dev() -> int:
+    return torch.cuda.current_device() if torch.cuda.is_available() else -1
 
 
 # ------------------------------------------------------------------------------------------------
@@ -203,7 +209,7 @@ class TurboBase(torch.nn.Module):
 
     # ---- engine lifecycle -------------------------------------------------------------------------
     def _get_engine(self) -> i2it.Engine:
-        key = (self.compute_dtype, torch.cuda.current_device() if torch.cuda.is_available() else -1)
+        key = (self.compute_dtype, _cur_dev())
         if self._engine is None or self._engine_key != key:
             if self._engine is not None:
                 self._engine.close()
@@ -225,7 +231,7 @@ class TurboBase(torch.nn.Module):
         return eng
 
     # ---- text ----------------------------------------------------------------------------------------
-    def _encode_text(self, prompt=None, tokens=None, device="cuda") -> torch.Tensor:
+    def _encode_text(self, prompt=None, tokens=None, device=None) -> torch.Tensor:
         """caption_enc = text_encoder(tokens)[0]; cached per distinct prompt / token tensor."""
         if prompt is not None:
             key = ("p", prompt if isinstance(prompt, str) else tuple(prompt), self.compute_dtype)
@@ -237,6 +243,7 @@ class TurboBase(torch.nn.Module):
         if prompt is not None:
             tokens = self.tokenizer(prompt, max_length=self.tokenizer.model_max_length, padding="max_length",
                                     truncation=True, return_tensors="pt").input_ids
+        device = device or DEVICE
         enc = self.text_encoder.to(device)
         with torch.no_grad():
             emb = enc(tokens.to(device))[0]
@@ -261,7 +268,7 @@ class TurboBase(torch.nn.Module):
         the result is returned in a fresh tensor (never aliased across calls).  The text embedding is not an input of the
         graph: its projections are cached on the engine (_bind_text)."""
         self._bind_text(eng, text)
-        key = (tuple(x.shape), x.dtype, eps.dtype, noise is not None, torch.cuda.current_device())
+        key = (tuple(x.shape), x.dtype, eps.dtype, noise is not None, _cur_dev())
         st = self.__dict__.setdefault("_stage", {}).get(key)
         if st is None:
             st = {"x": torch.empty_like(x), "eps": torch.empty_like(eps), "out": torch.empty_like(x),
@@ -283,7 +290,7 @@ class TurboBase(torch.nn.Module):
     def _prep(t: Optional[torch.Tensor], dtype) -> Optional[torch.Tensor]:
         if t is None:
             return None
-        return t.to(device="cuda", dtype=dtype).contiguous()
+        return t.to(device=DEVICE, dtype=dtype).contiguous()
 
 
 def load_sd_turbo_base(sd: Dict[str, torch.Tensor], which: List[str]) -> bool:

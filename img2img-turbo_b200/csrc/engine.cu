@@ -1226,16 +1226,24 @@ __global__ void stage_to_nchw_f32_kernel(const uint16_t* x, int ld, int C, long 
                    : __half2float(*reinterpret_cast<const __half*>(&v));
 }
 
-void Engine::read_stage(const std::string& name, float* dst, size_t dst_elems, int dims[4]) {
+void Engine::read_stage(const std::string& name_in, float* dst, size_t dst_elems, int dims[4]) {
   I2IT_CHECK(last_plan_ != nullptr, "no forward has run yet");
+  // "name@i" selects image i of the stage (large-batch stages do not fit a test's scratch buffer)
+  std::string name = name_in;
+  int pick = -1;
+  const size_t at = name.find('@');
+  if (at != std::string::npos) { pick = atoi(name.c_str() + at + 1); name = name.substr(0, at); }
   auto it = last_plan_->stages.find(name);
   I2IT_CHECK(it != last_plan_->stages.end(), "unknown stage '" + name + "' (was keep_stages set?)");
   const Act& a = it->second;
-  dims[0] = a.N; dims[1] = a.C; dims[2] = a.H; dims[3] = a.W;
-  const long long HW = static_cast<long long>(a.H) * a.W, total = HW * a.C * a.N;
+  I2IT_CHECK(pick < a.N, "read_stage: image index out of range");
+  const int n = pick >= 0 ? 1 : a.N;
+  dims[0] = n; dims[1] = a.C; dims[2] = a.H; dims[3] = a.W;
+  const long long HW = static_cast<long long>(a.H) * a.W, total = HW * a.C * n;
   I2IT_CHECK(static_cast<size_t>(total) <= dst_elems, "read_stage: destination too small");
   I2IT_CUDA(cudaDeviceSynchronize());
-  stage_to_nchw_f32_kernel<<<ceil_div(total, 256), 256>>>(a.p, a.ld, a.C, HW, total, dst, dtype == DT_BF16);
+  const uint16_t* src = a.p + (pick >= 0 ? static_cast<long long>(pick) * a.img() : 0);
+  stage_to_nchw_f32_kernel<<<ceil_div(total, 256), 256>>>(src, a.ld, a.C, HW, total, dst, dtype == DT_BF16);
   I2IT_CUDA(cudaDeviceSynchronize());
 }
 

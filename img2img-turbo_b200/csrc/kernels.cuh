@@ -389,10 +389,11 @@ __global__ void latent_sample_kernel(const T* __restrict__ mom, int ldm, const T
 // (/root/reference/src/pix2pix_turbo.py:200-203): x0 = (x - s1*eps_hat)/sa.
 //   three_round == 0  Pix2Pix_Turbo: `timesteps` is a 1-D tensor, so alphas_cumprod[t] is a dimensioned fp32 tensor and the
 //                     whole step is promoted to fp32, then rounded once by .to(model_pred.dtype)  (pix2pix_turbo.py:162,200-201)
-//   three_round == 1  CycleGAN_Turbo: `timesteps[i]` is 0-dim, alphas_cumprod[t] is a 0-dim CPU fp32 tensor, so every op stays
-//                     in the activation dtype with fp32 op-math: round(s1*e), round(x - .), round(. * (1/sa))  — torch's CUDA
-//                     mul/div kernels take a CPU scalar operand in fp32 and divide by multiplying with the fp32 reciprocal
-//                     (/root/reference/src/cyclegan_turbo.py:205); tests/test_gpu_e2e.py checks this bit for bit against torch.
+//   three_round == 1  CycleGAN_Turbo: `timesteps[i]` is 0-dim, so alphas_cumprod[t] (moved to the GPU by make_1step_sched,
+//                     /root/reference/src/model.py:10) is a 0-dim CUDA fp32 tensor: it does not promote the fp16/bf16 operands,
+//                     torch casts it to the activation dtype and every op rounds: c1 = round(s1), c2 = round(sa);
+//                     round(c1*e), round(x - .), round(. / c2) with fp32 op-math  (/root/reference/src/cyclegan_turbo.py:205).
+//                     tests/test_gpu_boundary.py checks this bit for bit against the same torch expression on the GPU.
 template <typename T>
 __global__ void ddpm_step_kernel(const T* __restrict__ zin /*NHWC8*/, const T* __restrict__ pred, int ldp,
                                  float s1, float sa, float inv_sf, T* __restrict__ dec_in /*NHWC8*/,
@@ -401,16 +402,16 @@ __global__ void ddpm_step_kernel(const T* __restrict__ zin /*NHWC8*/, const T* _
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const long long n = i / HW, p = i % HW;
-  const float inv_sa = 1.0f / sa;
   float o[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const float x = Elem<T>::to_f(zin[i * 8 + c]), e = Elem<T>::to_f(pred[i * ldp + c]);
     T x0t;
     if (three_round) {
-      const float t1 = Elem<T>::to_f(Elem<T>::from_f(s1 * e));
+      const float c1 = Elem<T>::to_f(Elem<T>::from_f(s1)), c2 = Elem<T>::to_f(Elem<T>::from_f(sa));
+      const float t1 = Elem<T>::to_f(Elem<T>::from_f(c1 * e));
       const float t2 = Elem<T>::to_f(Elem<T>::from_f(x - t1));
-      x0t = Elem<T>::from_f(t2 * inv_sa);
+      x0t = Elem<T>::from_f(t2 / c2);
     } else {
       x0t = Elem<T>::from_f((x - s1 * e) / sa);                  // x_denoised.to(dtype)
     }

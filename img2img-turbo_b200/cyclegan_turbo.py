@@ -18,6 +18,7 @@ import torch.nn as nn
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import i2it  # noqa: E402
 import weights as W  # noqa: E402
+import _host  # noqa: E402
 from _host import NetHandle, TurboBase, load_sd_turbo_base  # noqa: E402
 from model import download_url  # noqa: E402
 
@@ -139,7 +140,7 @@ class CycleGAN_Turbo(TurboBase):
         B, _, H, Wd = x.shape
         xd = self._prep(x, dt)
         if eps is None:
-            eps = torch.randn((B, 4, H // 8, Wd // 8), device="cuda", dtype=dt)   # latent_dist.sample()
+            eps = torch.randn((B, 4, H // 8, Wd // 8), device=_host.DEVICE, dtype=dt)   # latent_dist.sample()
         eps = self._prep(eps, dt)
         text = self._prep(text_emb, dt)
         if text.shape[0] not in (1, B):
@@ -188,10 +189,10 @@ class CycleGAN_Turbo(TurboBase):
         assert direction in ["a2b", "b2a"]
         dt = self.compute_dtype
         text = self._prep(caption_emb if caption_emb is not None else self._encode_text(caption), dt)
-        x = images_u8.to(device="cuda", non_blocking=True).contiguous()
+        x = images_u8.to(device=_host.DEVICE, non_blocking=True).contiguous()
         B, H, Wd, _ = x.shape
         if eps is None:
-            eps = torch.randn((B, 4, H // 8, Wd // 8), device="cuda", dtype=dt)
+            eps = torch.randn((B, 4, H // 8, Wd // 8), device=_host.DEVICE, dtype=dt)
         eps = self._prep(eps, dt)
         eng = self._finalize(1.0, 1.0, 1.0, -1.0)
         return self._staged_forward(eng, x, text, eps, direction=i2it.A2B if direction == "a2b" else i2it.B2A,

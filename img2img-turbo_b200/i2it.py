@@ -239,7 +239,10 @@ class Engine:
         self._check(self.lib.i2it_workspace_bytes(self._h, B, H, W, C.byref(n)), "i2it_workspace_bytes")
         return n.value
 
-    def read_stage(self, name: str, max_elems: int = 1 << 28) -> torch.Tensor:
+    def read_stage(self, name: str, max_elems: int = 1 << 26, image: Optional[int] = None) -> torch.Tensor:
+        """fp32 NCHW copy of a named stage of the last forward (keep_stages engines); image=i reads one image of the batch."""
+        if image is not None:
+            name = f"{name}@{int(image)}"
         dims = (C.c_int * 4)()
         buf = torch.empty(max_elems, dtype=torch.float32, device="cuda")
         self._check(self.lib.i2it_read_stage(self._h, name.encode(), _ptr(buf), max_elems, dims), f"i2it_read_stage({name})")

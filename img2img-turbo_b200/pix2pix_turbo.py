@@ -21,6 +21,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import i2it  # noqa: E402
 import weights as W  # noqa: E402
+import _host  # noqa: E402
 from _host import NetHandle, TurboBase, load_sd_turbo_base  # noqa: E402
 from model import download_url  # noqa: E402
 
@@ -166,8 +167,8 @@ class Pix2Pix_Turbo(TurboBase):
         x = self._prep(c_t, dt)
         if eps is None:
             # latent_dist.sample(): randn from the global RNG on the device, in the activation dtype
-            eps = torch.randn((B, 4, H // 8, Wd // 8), device="cuda", dtype=dt)
-            torch.randn((B, 4, H // 8, Wd // 8), device="cuda", dtype=dt)   # DDPM variance noise: drawn, x1e-10, discarded
+            eps = torch.randn((B, 4, H // 8, Wd // 8), device=_host.DEVICE, dtype=dt)
+            torch.randn((B, 4, H // 8, Wd // 8), device=_host.DEVICE, dtype=dt)   # DDPM variance noise: drawn, x1e-10, discarded
         eps = self._prep(eps, dt)
         if caption_enc.shape[0] not in (1, B):
             raise ValueError("prompt batch must be 1 or match the image batch")
@@ -198,11 +199,11 @@ class Pix2Pix_Turbo(TurboBase):
         assert (prompt is None) != (prompt_tokens is None), "Either prompt or prompt_tokens should be provided"
         dt = self.compute_dtype
         caption_enc = self._encode_text(prompt, prompt_tokens)
-        x = images_u8.to(device="cuda", non_blocking=True).contiguous()
+        x = images_u8.to(device=_host.DEVICE, non_blocking=True).contiguous()
         B, H, Wd, _ = x.shape
         if eps is None:
-            eps = torch.randn((B, 4, H // 8, Wd // 8), device="cuda", dtype=dt)
-            torch.randn((B, 4, H // 8, Wd // 8), device="cuda", dtype=dt)
+            eps = torch.randn((B, 4, H // 8, Wd // 8), device=_host.DEVICE, dtype=dt)
+            torch.randn((B, 4, H // 8, Wd // 8), device=_host.DEVICE, dtype=dt)
         eps = self._prep(eps, dt)
         mode = i2it.IN_SKETCH if sketch else i2it.IN_UNIT
         if deterministic:

@@ -221,3 +221,97 @@ print('rank', os.environ['RANK'], 'ok')
                         "127.0.0.1", "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_save_model_uses_peft_key_names_the_reference_loader_expects(tmp_path):
+    """the reference copies the checkpoint keys into vae.state_dict()/unet.state_dict() of peft-wrapped models and
+    loads STRICTLY (pix2pix_turbo.py:66-78): base weights of LoRA-wrapped layers must be spelled `X.base_layer.weight`."""
+    import weights as W
+    from pix2pix_turbo import Pix2Pix_Turbo
+    m = Pix2Pix_Turbo(cfg=W.TINY, text_stack=_text_stack(), twin=True)
+    p = str(tmp_path / "m.pkl")
+    m.save_model(p)
+    ck = torch.load(p)
+    vae = ck["state_dict_vae"]
+    for i in range(1, 5):                                               # skip convs are LoRA targets (pix2pix_turbo.py:143-147)
+        assert f"decoder.skip_conv_{i}.base_layer.weight" in vae and f"decoder.skip_conv_{i}.weight" not in vae
+        assert f"decoder.skip_conv_{i}.lora_A.vae_skip.weight" in vae
+    for k in vae:                                                       # every wrapped layer's base tensors carry the infix
+        if k.endswith((".weight", ".bias")) and ".lora_" not in k:
+            assert ".base_layer." in k, k
+    unet = ck["state_dict_unet"]
+    # TwinConv conv_in is not a LoRA target: plain names (reference filter `"conv_in" in k`)
+    assert "conv_in.conv_in_pretrained.weight" in unet and "conv_in.conv_in_curr.bias" in unet
+    assert all(("lora" in k) or ("conv_in" in k) for k in unet)
+    # and our own loader reads that spelling back
+    with pytest.warns(UserWarning):
+        m2 = Pix2Pix_Turbo(pretrained_path=p, cfg=W.TINY, text_stack=_text_stack())
+    assert m2._twin and torch.equal(m2._sd["vae.decoder.skip_conv_1.weight"], m._sd["vae.decoder.skip_conv_1.weight"])
+
+
+def test_checkpoint_decides_which_layers_get_adapters(tmp_path):
+    """adapters exist only where the checkpoint has them; no layer keeps a seeded random adapter."""
+    import weights as W
+    from pix2pix_turbo import Pix2Pix_Turbo
+    m = Pix2Pix_Turbo(cfg=W.TINY, text_stack=_text_stack())
+    p = str(tmp_path / "m.pkl")
+    m.save_model(p)
+    ck = torch.load(p)
+    lora = [k for k in ck["state_dict_unet"] if "lora" in k]
+    keep = set(lora[:6])
+    ck["state_dict_unet"] = {k: v for k, v in ck["state_dict_unet"].items() if k in keep or "lora" not in k}
+    ck["unet_lora_target_modules"] = ["to_q"]
+    torch.save(ck, p)
+    with pytest.warns(UserWarning):
+        m2 = Pix2Pix_Turbo(pretrained_path=p, cfg=W.TINY, text_stack=_text_stack())
+    got = {k for k in m2._sd if k.startswith("unet.") and ".lora_" in k}
+    assert got == {"unet." + k for k in keep}
+    assert m2.target_modules_unet == ["to_q"]
+
+
+def test_named_cyclegan_model_does_not_run_on_random_weights(tmp_path, monkeypatch):
+    """a named pretrained model whose checkpoint cannot be loaded raises (as Pix2Pix_Turbo does) unless the caller
+    opts in; a partial download never poses as the checkpoint."""
+    import weights as W
+    import cyclegan_turbo as C
+    import model as M
+
+    def boom(url, outf):
+        raise OSError("network unreachable")
+    monkeypatch.setattr(C, "download_url", boom)
+    with pytest.raises(RuntimeError, match="allow_synthetic_weights"):
+        C.CycleGAN_Turbo(pretrained_name="day_to_night", cfg=W.TINY, text_stack=_text_stack(), ckpt_folder=str(tmp_path))
+    with pytest.warns(UserWarning):
+        m = C.CycleGAN_Turbo(pretrained_name="day_to_night", cfg=W.TINY, text_stack=_text_stack(), ckpt_folder=str(tmp_path),
+                             allow_synthetic_weights=True)
+    assert m.caption == "driving in the night" and m.direction == "a2b"
+    # corrupt / truncated file on disk: torch.load fails -> raises too
+    bad = tmp_path / "day2night.pkl"
+    bad.write_bytes(b"not a pickle")
+    monkeypatch.setattr(C, "download_url", M.download_url)               # "Skipping download": the file exists
+    with pytest.raises(RuntimeError, match="allow_synthetic_weights"):
+        C.CycleGAN_Turbo(pretrained_name="day_to_night", cfg=W.TINY, text_stack=_text_stack(), ckpt_folder=str(tmp_path))
+
+    class Resp:
+        def raise_for_status(self):
+            pass
+
+        def iter_content(self, n):
+            yield b"abc"
+            raise ConnectionError("dropped")
+    import types
+    monkeypatch.setitem(sys.modules, "requests", types.SimpleNamespace(get=lambda url, stream=True: Resp()))
+    target = tmp_path / "x.pkl"
+    with pytest.raises(ConnectionError):
+        M.download_url("http://example.invalid/x.pkl", str(target))
+    assert not target.exists()                                           # only a .part file is left behind
+
+
+def test_fp32_model_warns_that_it_computes_in_bf16():
+    import weights as W
+    from pix2pix_turbo import Pix2Pix_Turbo
+    m = Pix2Pix_Turbo(cfg=W.TINY, text_stack=_text_stack())
+    with pytest.warns(UserWarning, match="bf16"):
+        assert m.compute_dtype == torch.bfloat16
+    m.half()
+    assert m.compute_dtype == torch.float16
