@@ -213,9 +213,13 @@ class TurboBase(torch.nn.Module):
         if self._engine is None or self._engine_key != key:
             if self._engine is not None:
                 self._engine.close()
+            te = self._text_encoder_spec()
             eng = i2it.Engine(self.compute_dtype, self.MODEL_KIND, cfg=self._cfg, keep_stages=self._keep_stages,
-                              use_cuda_graph=self._use_graph)
+                              use_cuda_graph=self._use_graph, **({"text_heads": te["heads"], "text_act": te["act"]} if te else {}))
             eng.load_state_dict(self._sd)
+            if te:      # the CLIP text tower runs on the engine too: same tensors, transformers key names
+                eng.load_state_dict({"text_encoder." + k: v for k, v in self.text_encoder.state_dict().items()})
+            self._text_on_engine = bool(te)
             for name, s in self._adapter_scales.items():
                 eng.set_adapter_scale(name, s)
             self._engine, self._engine_key, self._final_key = eng, key, None
@@ -231,6 +235,21 @@ class TurboBase(torch.nn.Module):
         return eng
 
     # ---- text ----------------------------------------------------------------------------------------
+    def _text_encoder_spec(self):
+        """{"heads", "act", "hidden"} if the text encoder is a CLIP text tower libi2it can run (64-wide heads, gelu / quick_gelu,
+        width <= 1280), else None (the stock transformers module is called instead)."""
+        enc = self.text_encoder
+        c = getattr(enc, "config", None)
+        if enc is None or c is None or os.environ.get("I2IT_TORCH_TEXT"):
+            return None
+        try:
+            hidden, heads, act = int(c.hidden_size), int(c.num_attention_heads), str(c.hidden_act)
+        except Exception:
+            return None
+        if heads * 64 != hidden or hidden > 1280 or act not in ("gelu", "quick_gelu") or int(c.max_position_embeddings) != 77:
+            return None
+        return {"heads": heads, "act": act, "hidden": hidden}
+
     def _encode_text(self, prompt=None, tokens=None, device=None) -> torch.Tensor:
         """caption_enc = text_encoder(tokens)[0]; cached per distinct prompt / token tensor."""
         if prompt is not None:
@@ -244,10 +263,17 @@ class TurboBase(torch.nn.Module):
             tokens = self.tokenizer(prompt, max_length=self.tokenizer.model_max_length, padding="max_length",
                                     truncation=True, return_tensors="pt").input_ids
         device = device or DEVICE
-        enc = self.text_encoder.to(device)
-        with torch.no_grad():
-            emb = enc(tokens.to(device))[0]
-        emb = emb.to(self.compute_dtype).contiguous()
+        eng = self._get_engine() if (device == "cuda" and self._text_encoder_spec()) else None
+        if eng is not None and getattr(self, "_text_on_engine", False):
+            # text_encoder(tokens)[0] on the engine: same tensors, hand-written kernels (no torch modules on this path)
+            if self._final_key is None:      # the tower has no LoRA: any fold state will do, but the engine wants one
+                self._finalize(1.0, 1.0, 1.0, -1.0)
+            emb = eng.encode_text(tokens, self._text_encoder_spec()["hidden"])
+        else:
+            enc = self.text_encoder.to(device)
+            with torch.no_grad():
+                emb = enc(tokens.to(device))[0]
+            emb = emb.to(self.compute_dtype).contiguous()
         if len(self._text_cache) > 64:
             self._text_cache.clear()
         self._text_cache[key] = emb

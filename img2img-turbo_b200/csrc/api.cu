@@ -39,6 +39,8 @@ int i2it_default_config(i2it_config* c) {
   c->scaling_factor = 0.18215f;
   c->keep_stages = 0;
   c->use_cuda_graph = 1;
+  c->text_heads = 16;
+  c->text_act = 0;
   return 0;
 }
 
@@ -112,6 +114,13 @@ int i2it_set_text(i2it_handle* h, const void* text_emb, int text_batch, void* st
   API_BEGIN(h)
   E.check_device_error();
   E.set_text(text_emb, text_batch, static_cast<cudaStream_t>(stream));
+  API_END
+}
+
+int i2it_encode_text(i2it_handle* h, const int32_t* tokens, int batch, void* out, void* stream) {
+  API_BEGIN(h)
+  E.check_device_error();
+  E.encode_text(reinterpret_cast<const int*>(tokens), batch, out, static_cast<cudaStream_t>(stream));
   API_END
 }
 

@@ -93,6 +93,9 @@ __device__ __forceinline__ float erf_as(float x) {
 }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f)); }
 
+// CLIP's quick_gelu: x * sigmoid(1.702 x)
+__device__ __forceinline__ float quick_gelu_f(float x) { return __fdividef(x, 1.0f + ex2_approx(-1.702f * 1.4426950408889634f * x)); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

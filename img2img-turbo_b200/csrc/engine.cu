@@ -122,7 +122,8 @@ Engine::Engine(const i2it_config& c) : cfg(c), dtype(c.dtype) {
 #ifdef I2IT_TRACE_BUILD
   trace_on = std::getenv("I2IT_TRACE") != nullptr;
 #endif
-  use_ostage = std::getenv("I2IT_NO_OSTG") == nullptr;
+  use_tmaout = std::getenv("I2IT_NO_TMAOUT") == nullptr;   // TMA-store epilogue (per-thread stores otherwise)
+  use_gnepi = std::getenv("I2IT_NO_GNEPI") == nullptr;     // GroupNorm statistics in the producing GEMM's epilogue
   pair_min_tiles = std::getenv("I2IT_PAIR_MIN_TILES") ? atoll(std::getenv("I2IT_PAIR_MIN_TILES")) : 2ll * num_sms;
   use_idres = std::getenv("I2IT_NO_IDRES") == nullptr;
   use_halo = std::getenv("I2IT_NO_HALO") == nullptr;   // 3x3 convs: one halo tile per k-chunk instead of nine shifted A boxes
@@ -142,6 +143,7 @@ Engine::Engine(const i2it_config& c) : cfg(c), dtype(c.dtype) {
 Engine::~Engine() {
   plans_.clear();
   textkv_.clear();
+  textenc_.clear();
   free_prepared();
   for (auto& kv : w_) cudaFree(kv.second.d);
   if (err_host_) cudaFreeHost(err_host_);
@@ -223,6 +225,7 @@ void Engine::finalize(float lw_unet, float lw_vae, float skip_gamma, float twin_
   lw_unet_ = lw_unet; lw_vae_ = lw_vae; skip_gamma_ = skip_gamma; twin_r_ = twin_r;
   plans_.clear();
   textkv_.clear();                 // cached cross-attention operands were projected with the old (LoRA-scaled) weights
+  textenc_.clear();
   last_plan_ = nullptr;
   free_prepared();
   finalized_ = true;
@@ -428,14 +431,17 @@ PW Engine::prep_subpixel(const std::string& name) {
 }
 
 // nearest-2x upsample + conv3x3 (+ optional folded 1x1 second source at output resolution) as four parity-phase launches
-Act Engine::conv_up2x(Plan& P, const Act& x, const PW& wsub, const Act* x2, const PW* w2) {
+Act Engine::conv_up2x(Plan& P, const Act& x, const PW& wsub, const Act* x2, const PW* w2, bool gn_out) {
   Act out = alloc_act(P, x.N, 2 * x.H, 2 * x.W, wsub.rows);
   for (int ph = 0; ph < 4; ++ph) {
     ConvOpts o;
     o.subpixel_phase = ph;
     o.out = &out;
     o.x2 = x2; o.w2 = w2;
-    conv(P, x, wsub, o);
+    o.gn_out = gn_out;
+    o.gn_share = out.gn;                 // phase 0 creates the partial buffer, phases 1..3 fill their slot ranges
+    Act y = conv(P, x, wsub, o);
+    out.gn = y.gn;
   }
   return out;
 }
@@ -517,13 +523,18 @@ Act Engine::alloc_act(Plan& P, int N, int H, int W, int C, int ld, bool zero_per
   return a;
 }
 
-int Engine::pick_bn(long long m_tiles, int N, bool) const {
+int Engine::pick_bn(long long m_tiles, int N, int step) const {
   if (N <= 16) return 16;
-  static const int cand[] = {256, 224, 192, 160, 128, 112, 96, 80, 64, 48, 32, 16};
-  int best = 16;
+  static const int cand_any[] = {256, 224, 192, 160, 128, 112, 96, 80, 64, 48, 32, 16};
+  static const int cand_64[] = {256, 192, 128, 64};
+  static const int cand_128[] = {256, 128};
+  const int* cand = step == 128 ? cand_128 : (step == 64 ? cand_64 : cand_any);
+  const int ncand = step == 128 ? 2 : (step == 64 ? 4 : 12);
+  int best = cand[ncand - 1];
   double best_cost = 1e30;
-  for (int bn : cand) {
-    if (bn > round_up(N, 16)) continue;
+  for (int i = 0; i < ncand; ++i) {
+    const int bn = cand[i];
+    if (bn > round_up(N, step > 0 ? step : 16)) continue;
     const long long tiles = m_tiles * ceil_div(N, bn);
     const long long waves = (tiles + num_sms - 1) / num_sms;
     // a tile's time is bounded by its L2->SMEM traffic (A 128 rows + B bn rows per k-step) as much as by the MMA (bn)
@@ -532,6 +543,25 @@ int Engine::pick_bn(long long m_tiles, int N, bool) const {
   }
   return best;
 }
+
+// The TMA-store epilogue handles 16-bit row-major outputs whose channel count and tile width are whole 64-column rounds (128
+// accumulator columns for GEGLU) with 16-byte aligned rows; everything else keeps per-thread stores.
+bool Engine::tma_eligible(const TapGemmParams& p, bool out_from_io) const {
+  if (!use_tmaout || out_from_io || p.out_fp32 || p.ocol != 1 || p.bias_mode == TG_BIAS_ROW || p.out == nullptr) return false;
+  const int acols = (p.act == TG_ACT_GEGLU) ? 128 : 64;
+  if (p.N % acols != 0 || p.BN % acols != 0) return false;
+  if (reinterpret_cast<uintptr_t>(p.out) % 16 != 0) return false;
+  for (int d = 0; d < 4; ++d)
+    if (p.ext[d] > 1 && (p.ostride[d] * 2) % 16 != 0) return false;
+  if (p.res) {
+    if (p.rcol != 1 || reinterpret_cast<uintptr_t>(p.res) % 16 != 0 || p.act == TG_ACT_GEGLU) return false;
+    for (int d = 0; d < 4; ++d)
+      if (p.ext[d] > 1 && (p.rstride[d] * 2) % 16 != 0) return false;
+  }
+  return true;
+}
+
+static void fill_strides(TmapSpec& s);
 
 void Engine::launch_gemm(Plan& P, const TmapSpec& sa, TmapSpec sb, const TapGemmParams& p_in, bool out_from_io,
                          const char* kind, double k_valid, double bytes, const TmapSpec* sa2p, const TmapSpec* sb2p,
@@ -569,11 +599,31 @@ void Engine::launch_gemm(Plan& P, const TmapSpec& sa, TmapSpec sb, const TapGemm
     grid = static_cast<int>(std::min<long long>(total_tiles, num_sms));
   }
   char shp[160];
-  snprintf(shp, sizeof shp, "M=%.0f N=%d K=%.0f taps=%d BN=%d tiles=%lld grid=%d%s", m_valid, p.N, k_valid, p.num_taps, p.BN,
-           total_tiles, grid, pair ? (p.halo ? " pair halo" : " pair") : "");
-  // staged (coalesced) output stores pay off where the epilogue is the tile's critical path and the extra shared-memory
-  // pass is cheap: the 3x3 / sub-pixel convs with N <= 256 (measured: -7 % there, +5..15 % on the small-K linears / GEGLU)
-  p.ostage = (use_ostage && p.num_taps >= 5 && p.N <= 256) ? 1 : 0;
+  snprintf(shp, sizeof shp, "M=%.0f N=%d K=%.0f taps=%d BN=%d tiles=%lld grid=%d%s%s%s", m_valid, p.N, k_valid, p.num_taps, p.BN,
+           total_tiles, grid, pair ? (p.halo ? " pair halo" : " pair") : "", tma_eligible(p, out_from_io) ? " tma" : "",
+           (p.gn_part && tma_eligible(p, out_from_io)) ? " gn" : "");
+  // TMA-store epilogue: the output tensor map has the tile's row dims (extents = logical extents, so ragged edges are clipped
+  // by the hardware) and a box of 64 columns x the 32 rows one epilogue warp owns
+  p.tma_out = tma_eligible(p, out_from_io) ? 1 : 0;
+  if (!p.tma_out) p.gn_part = nullptr;
+  CUtensorMap to = ta;
+  if (p.tma_out) {
+    TmapSpec so;
+    so.base = p.out;
+    so.dim[0] = (p.act == TG_ACT_GEGLU) ? p.N / 2 : p.N;
+    int left = 32;
+    for (int d = 0; d < 4; ++d) {
+      so.dim[d + 1] = static_cast<uint64_t>(std::max(1, p.ext[d]));
+      so.stride[d] = static_cast<uint64_t>(p.ostride[d]) * 2ull;
+      const int sb = std::min(p.box[d], left);
+      so.box[d + 1] = static_cast<uint32_t>(sb);
+      left /= sb;
+    }
+    I2IT_CHECK(left == 1, "TMA-store box: the tile's row box does not factor into 32-row warp boxes");
+    so.box[0] = 64;
+    fill_strides(so);
+    to = encode_tmap(so, dtype);
+  }
   p.trace = nullptr;
   if (trace_on) {   // diagnostic timeline (I2IT_TRACE=1): 16 clock64 stamps per CTA, dumped to stderr after each forward
     p.trace = static_cast<unsigned long long*>(dmalloc(static_cast<size_t>(grid) * 16 * sizeof(unsigned long long)));
@@ -581,16 +631,16 @@ void Engine::launch_gemm(Plan& P, const TmapSpec& sa, TmapSpec sb, const TapGemm
     P.traces.push_back({p.trace, grid, std::string(kind) + " " + shp});
   }
   if (pair) {
-    add_op(P, [ta, tb, ta2, tb2, th, p, grid, dt, out_from_io, plan](cudaStream_t st) {
+    add_op(P, [ta, tb, ta2, tb2, th, to, p, grid, dt, out_from_io, plan](cudaStream_t st) {
       TapGemmParams q = p;
       if (out_from_io) q.out = plan->io.out;
-      DISPATCH_T(dt, (launch_k(tapgemm2_kernel<T>, dim3(grid), dim3(TG_THREADS), TG2_SMEM, st, 2, ta, tb, ta2, tb2, th, q)));
+      DISPATCH_T(dt, (launch_k(tapgemm2_kernel<T>, dim3(grid), dim3(TG_THREADS), TG2_SMEM, st, 2, ta, tb, ta2, tb2, th, to, q)));
     }, kind, 2.0 * m_valid * p.N * k_valid, bytes, shp);
   } else {
-    add_op(P, [ta, tb, ta2, tb2, p, grid, dt, out_from_io, plan](cudaStream_t st) {
+    add_op(P, [ta, tb, ta2, tb2, to, p, grid, dt, out_from_io, plan](cudaStream_t st) {
       TapGemmParams q = p;
       if (out_from_io) q.out = plan->io.out;
-      DISPATCH_T(dt, (launch_k(tapgemm_kernel<T>, dim3(grid), dim3(TG_THREADS), TG_SMEM, st, 0, ta, tb, ta2, tb2, q)));
+      DISPATCH_T(dt, (launch_k(tapgemm_kernel<T>, dim3(grid), dim3(TG_THREADS), TG_SMEM, st, 0, ta, tb, ta2, tb2, to, q)));
     }, kind, 2.0 * m_valid * p.N * k_valid, bytes, shp);
   }
 }
@@ -724,7 +774,12 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o_in) {
 
   const long long m_tiles = 1ll * p.tdim[0] * p.tdim[1] * p.tdim[2] * p.tdim[3];
   p.N = gemm_n;
-  p.BN = pick_bn(m_tiles, gemm_n, false);
+  {
+    // whole 64-column store rounds (128 accumulator columns for GEGLU) when the output can take the TMA-store epilogue
+    const int acols = (o.act == TG_ACT_GEGLU) ? 128 : 64;
+    const bool rounds = use_tmaout && !o.to_io_out_nchw && !o.out_fp32 && gemm_n % acols == 0 && (ldo % 8) == 0;
+    p.BN = pick_bn(m_tiles, gemm_n, rounds ? acols : 0);
+  }
   p.n_tiles = ceil_div(gemm_n, p.BN);
   sb.box[0] = 64; sb.box[1] = p.BN; sb.box[2] = 1; sb.box[3] = 1; sb.box[4] = 1;
   p.num_taps = taps;
@@ -756,6 +811,39 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o_in) {
   p.alpha = o.alpha;
   p.act = o.act;
   p.err = d_err;
+
+  // GroupNorm statistics of the output in this GEMM's epilogue (the consumer is a GroupNorm): needs the TMA-store path, a
+  // 32-group channel count, and m-tiles that never straddle two images (so a 32-row slot belongs to one image)
+  if ((o.gn_out || o.gn_share) && use_gnepi && outc % 64 == 0 && tma_eligible(p, o.to_io_out_nchw) && o.act != TG_ACT_GEGLU) {
+    long long mt_img = 0;                 // m-tiles per image
+    int images = x.N;
+    if (o.gn_rows_per_image > 0) {        // flattened token matrix: 128-row tiles
+      if (o.gn_rows_per_image % 128 == 0 && x.rows() % o.gn_rows_per_image == 0) {
+        mt_img = o.gn_rows_per_image / 128;
+        images = static_cast<int>(x.rows() / o.gn_rows_per_image);
+      }
+    } else if (tn == 1) {
+      mt_img = (o.stride == 1) ? 1ll * p.tdim[0] * p.tdim[1] : 1ll * p.tdim[0] * p.tdim[2];
+    }
+    if (mt_img > 0) {
+      const int cgrp = outc / 32;
+      const int red = (cgrp == 4 || cgrp == 8 || cgrp == 16) ? cgrp : 2;
+      std::shared_ptr<GnPart> g = o.gn_share;
+      if (!g) {
+        g = std::make_shared<GnPart>();
+        g->red = red; g->C = outc; g->images = images; g->phases = sub ? 4 : 1;
+        g->slots_per_image = static_cast<int>(mt_img * 4);
+        g->hold = alloc_raw(P, static_cast<size_t>(g->phases) * images * g->slots_per_image * (outc / red) * 2 * sizeof(float));
+        g->buf = static_cast<float*>(g->hold.get());
+      }
+      I2IT_CHECK(g->C == outc && g->slots_per_image == mt_img * 4 && g->images == images, "conv: shared GroupNorm partials mismatch");
+      p.gn_part = g->buf;
+      p.gn_red = g->red;
+      p.gn_slot0 = sub ? o.subpixel_phase * images * g->slots_per_image : 0;
+      p.gn_mtiles = static_cast<int>(mt_img * images);
+      out.gn = g;
+    }
+  }
 
   TmapSpec sa2, sb2;
   double k2 = 0;
@@ -805,10 +893,12 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o_in) {
   return out;
 }
 
-Act Engine::linear(Plan& P, const Act& x, const PW& w, const Act* res, int act) {
+Act Engine::linear(Plan& P, const Act& x, const PW& w, const Act* res, int act, bool gn_out) {
   ConvOpts o;
   o.ksize = 1;
   o.act = act;
+  o.gn_out = gn_out;
+  o.gn_rows_per_image = static_cast<long long>(x.H) * x.W;
   Act xr = x.as_rows(), rr;
   if (res) { rr = res->as_rows(); o.res = &rr; }
   Act y = conv(P, xr, w, o);
@@ -838,32 +928,45 @@ Act Engine::group_norm(Plan& P, const Act& x, const NormW& nw, float eps, bool s
   const int ldx = x.ld, ldy = y.ld, N = x.N, dt = dtype, isilu = silu ? 1 : 0;
   const float* g = nw.g;
   const float* b = nw.b;
-  add_op(P, [=](cudaStream_t st) {
-    DISPATCH_T(dt, (launch_k(gn_stats_kernel<T>, dim3(chunks, N), dim3(threads), static_cast<size_t>(rows) * 2 * C * sizeof(float), st, 0,
-                             reinterpret_cast<const T*>(xp), ximg, ldx, C, HW, cg, pix, d_part)));
-  }, "gn_stats", 0, 2.0 * N * HW * C);
   const double inv_count = 1.0 / (static_cast<double>(HW) * cg);
-  add_op(P, [=](cudaStream_t st) { launch_k(gn_finalize_kernel, dim3(N), dim3(1024), 0, st, 0, d_part, chunks, inv_count, eps, d_stats); }, "gn_final");
+  if (x.gn && use_gnepi && x.gn->C == C && x.gn->images == N) {
+    // the producer's epilogue already summed the tensor: reduce its per-slot partials (no pass over the tensor itself)
+    const GnPart gp = *x.gn;
+    const float* pb = gp.buf;
+    const int per_row = C / gp.red, epg = cg / gp.red;
+    add_op(P, [=](cudaStream_t st) {
+      launch_k(gn_finalize_part_kernel, dim3(32, N), dim3(256), 0, st, 0, pb, gp.phases, gp.images, gp.slots_per_image, per_row, epg,
+               inv_count, eps, d_stats);
+    }, "gn_final_part", 0, 8.0 * gp.phases * N * gp.slots_per_image * per_row);
+  } else {
+    add_op(P, [=](cudaStream_t st) {
+      DISPATCH_T(dt, (launch_k(gn_stats_kernel<T>, dim3(chunks, N), dim3(threads), static_cast<size_t>(rows) * 2 * C * sizeof(float), st, 0,
+                               reinterpret_cast<const T*>(xp), ximg, ldx, C, HW, cg, pix, d_part)));
+    }, "gn_stats", 0, 2.0 * N * HW * C);
+    add_op(P, [=](cudaStream_t st) { launch_k(gn_finalize_kernel, dim3(N), dim3(1024), 0, st, 0, d_part, chunks, inv_count, eps, d_stats); }, "gn_final");
+  }
   add_op(P, [=](cudaStream_t st) {
     DISPATCH_T(dt, (launch_k(gn_apply_kernel<T>, dim3(chunks, N), dim3(threads), 0, st, 0,
                        reinterpret_cast<const T*>(xp), ximg, ldx, reinterpret_cast<T*>(yp), yimg, ldy, C, HW, cg, pix,
                        d_stats, g, b, isilu)));
   }, "gn_apply", 0, 4.0 * N * HW * C);
-  return y;
+  return y;     // (y carries no statistics: it is a different tensor)
 }
 
-Act Engine::layer_norm(Plan& P, const Act& x, const NormW& nw) {
+Act Engine::layer_norm(Plan& P, const Act& x, const NormW& nw, bool to_io_out) {
   I2IT_CHECK(x.C == nw.C && x.C % 8 == 0 && x.C <= 1280, "layer_norm: C must be a multiple of 8 and <= 1280");
-  Act y = alloc_act(P, x.N, x.H, x.W, x.C);
+  Act y = to_io_out ? x : alloc_act(P, x.N, x.H, x.W, x.C);       // to_io_out: dense rows straight into the caller's buffer
   const long long rows = x.rows();
   const uint16_t* xp = x.p;
-  uint16_t* yp = y.p;
-  const int ldx = x.ld, ldy = y.ld, C = x.C, dt = dtype;
+  uint16_t* yp = to_io_out ? nullptr : y.p;
+  const int ldx = x.ld, ldy = to_io_out ? x.C : y.ld, C = x.C, dt = dtype;
   const float* g = nw.g;
   const float* b = nw.b;
+  Plan* plan = &P;
   add_op(P, [=](cudaStream_t st) {
+    uint16_t* dst = yp ? yp : static_cast<uint16_t*>(plan->io.out);
     DISPATCH_T(dt, (launch_k(layernorm_kernel<T>, dim3(ceil_div(rows * 32, 256)), dim3(256), 0, st, 0,
-                       reinterpret_cast<const T*>(xp), ldx, reinterpret_cast<T*>(yp), ldy, static_cast<int>(rows), C, g, b,
+                       reinterpret_cast<const T*>(xp), ldx, reinterpret_cast<T*>(dst), ldy, static_cast<int>(rows), C, g, b,
                        1e-5f)));
   }, "layernorm", 0, 4.0 * rows * C);
   return y;
@@ -1039,7 +1142,8 @@ Act Engine::attention(Plan& P, const Act& q, const Act& k, const Act& vt, int B,
   return out;
 }
 
-Act Engine::flash_attention(Plan& P, const Act& q, const Act& k, const Act& vt, int B, int Nq, int Nk, int heads, int kv_batch) {
+Act Engine::flash_attention(Plan& P, const Act& q, const Act& k, const Act& vt, int B, int Nq, int Nk, int heads, int kv_batch,
+                            bool causal) {
   I2IT_CHECK(kv_batch == B || kv_batch == 1, "attention: kv batch must be 1 or B");
   const int d = FA_D, C = heads * d;
   Act out = alloc_act(P, B, 1, Nq, C);
@@ -1070,6 +1174,7 @@ Act Engine::flash_attention(Plan& P, const Act& q, const Act& k, const Act& vt, 
   fp.ldo = out.ld;
   fp.idesc = make_idesc(dtype, FA_BN);
   fp.err = d_err;
+  fp.causal = causal ? 1 : 0;
   const CUtensorMap tq = encode_tmap(sq, dtype), tk = encode_tmap(sk, dtype), tv = encode_tmap(sv, dtype);
   const int grid = fp.q_tiles * heads * B, dt = dtype;
   char shp[96];
@@ -1100,6 +1205,70 @@ void Engine::set_text(const void* text, int text_batch, cudaStream_t st) {
   nvtxRangePop();
   I2IT_CUDA(cudaGetLastError());
   T.filled = true;
+}
+
+// CLIP text tower on the engine (transformers models/clip/modeling_clip.py CLIPTextTransformer.forward): token +
+// position embeddings, pre-LN transformer layers with CAUSAL self-attention (16 heads x 64 for SD-Turbo's OpenCLIP-H tower) and a
+// GELU MLP, final LayerNorm -> last_hidden_state, i.e. `text_encoder(tokens)[0]` of /root/reference/src/pix2pix_turbo.py:190-196.
+// Same kernels as the image path: tapgemm (fused q|k projection, V^T projection with row bias, GELU in the fc1 epilogue, residual
+// adds in the out_proj / fc2 epilogues), flash_attn with the causal flag, layernorm.
+void Engine::encode_text(const int* tokens, int batch, void* out, cudaStream_t st) {
+  I2IT_CHECK(finalized_, "i2it_finalize_weights must be called before i2it_encode_text");
+  I2IT_CHECK(tokens && out && batch > 0, "i2it_encode_text: bad arguments");
+  I2IT_CHECK(has_text_encoder(), "no text_encoder.* weights were registered (i2it_set_weight)");
+  auto& slot = textenc_[batch];
+  if (!slot) {
+    slot.reset(new Plan());
+    Plan& P = *slot;
+    const std::string te = "text_encoder.text_model";
+    const WT& tok = raw(te + ".embeddings.token_embedding", "weight");
+    const WT& pos = raw(te + ".embeddings.position_embedding", "weight");
+    const int C = static_cast<int>(tok.shape[1]), vocab = static_cast<int>(tok.shape[0]), ntok = static_cast<int>(pos.shape[0]);
+    I2IT_CHECK(C % 64 == 0 && C <= 1280, "text encoder width must be a multiple of 64 (64-wide heads) and <= 1280");
+    const int heads = cfg.text_heads > 0 ? cfg.text_heads : C / 64;
+    I2IT_CHECK(heads * 64 == C, "text encoder: head_dim must be 64");
+    const int act = cfg.text_act == 1 ? TG_ACT_QUICKGELU : TG_ACT_GELU;
+    int layers = 0;
+    while (has(te + ".encoder.layers." + std::to_string(layers) + ".layer_norm1.weight")) ++layers;
+    I2IT_CHECK(layers > 0, "text encoder: no layers found");
+    Act x = alloc_act(P, batch, 1, ntok, C);
+    {
+      const long long total = static_cast<long long>(batch) * ntok * (C / 8);
+      uint16_t* xp = x.p;
+      const float* tp = tok.d;
+      const float* pp = pos.d;
+      const int dt = dtype;
+      Plan* plan = &P;
+      add_op(P, [=](cudaStream_t s2) {
+        DISPATCH_T(dt, (launch_k(clip_embed_kernel<T>, dim3(ceil_div(total, 256)), dim3(256), 0, s2, 0,
+                           reinterpret_cast<const int*>(plan->io.x), tp, pp, reinterpret_cast<T*>(xp), C, ntok, vocab, total)));
+      }, "clip_embed", 0, 2.0 * total * 8 * 3);
+    }
+    for (int l = 0; l < layers; ++l) {
+      const std::string L = te + ".encoder.layers." + std::to_string(l);
+      Act n = layer_norm(P, x, norm(L + ".layer_norm1"));
+      Act qk = linear(P, n, prep(L + ".qk", {L + ".self_attn.q_proj", L + ".self_attn.k_proj"}));
+      Act vt = vt_proj(P, n, batch, ntok, prep(L + ".self_attn.v_proj", {L + ".self_attn.v_proj"}));
+      Act a = flash_attention(P, qk.slice(0, C), qk.slice(C, C), vt, batch, ntok, ntok, heads, batch, /*causal=*/true);
+      a.N = batch; a.H = 1; a.W = ntok;
+      x = linear(P, a, prep(L + ".self_attn.out_proj", {L + ".self_attn.out_proj"}), &x);
+      Act m = layer_norm(P, x, norm(L + ".layer_norm2"));
+      Act h = linear(P, m, prep(L + ".mlp.fc1", {L + ".mlp.fc1"}), nullptr, act);
+      x = linear(P, h, prep(L + ".mlp.fc2", {L + ".mlp.fc2"}), &x);
+    }
+    layer_norm(P, x, norm(te + ".final_layer_norm"), /*to_io_out=*/true);
+    P.keep.push_back(x.hold);
+    flush_prep();
+    I2IT_CUDA(cudaDeviceSynchronize());
+  }
+  Plan& P = *slot;
+  P.io.x = tokens;
+  P.io.out = out;
+  nvtxRangePushA("i2it:clip_text_encoder");
+  g_pdl.enabled = false; g_pdl.prev_is_kernel = false;
+  for (auto& op : P.ops) op(st);
+  nvtxRangePop();
+  I2IT_CUDA(cudaGetLastError());
 }
 
 void Engine::forward(const IO& io_in, int B, int H, int W, int direction, int text_batch, cudaStream_t st) {

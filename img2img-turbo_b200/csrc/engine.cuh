@@ -42,14 +42,23 @@ struct Pool {
   void put(void* p, size_t bytes) { free_.emplace(bytes, p); }
 };
 
+// GroupNorm partial statistics written by the epilogue of the GEMM that PRODUCED a tensor (see TapGemmParams::gn_part):
+// [phases][images][slots_per_image][C / red] x (sum, sum of squares), fp32
+struct GnPart {
+  std::shared_ptr<void> hold;
+  float* buf = nullptr;
+  int red = 2, slots_per_image = 0, C = 0, phases = 1, images = 0;
+};
+
 struct Act {                       // NHWC view, 2-byte elements
   std::shared_ptr<void> hold;
   uint16_t* p = nullptr;
   int N = 0, H = 0, W = 0, C = 0, ld = 0;
+  std::shared_ptr<GnPart> gn;      // statistics of this (whole) tensor, if its producer computed them
   long long img() const { return static_cast<long long>(H) * W * ld; }
   long long rows() const { return static_cast<long long>(N) * H * W; }
   Act as_rows() const { Act a = *this; a.W = static_cast<int>(rows()); a.N = 1; a.H = 1; return a; }
-  Act slice(int c0, int c) const { Act a = *this; a.p = p + c0; a.C = c; return a; }
+  Act slice(int c0, int c) const { Act a = *this; a.p = p + c0; a.C = c; a.gn = nullptr; return a; }
 };
 
 struct PW {                        // prepared (folded, re-laid-out) weight: [taps][rows][cin_pad] + fp32 bias
@@ -132,6 +141,9 @@ struct ConvOpts {
   const PW* w2 = nullptr;
   bool x2_identity = false;      // x2/w2 is the residual x identity trick: not algorithmic work (excluded from flop counts)
   int subpixel_phase = -1;       // >=0: this launch is parity phase (py*2+px) of a fused nearest-2x-upsample + 3x3 conv
+  bool gn_out = false;           // the consumer of the output is a GroupNorm: take its statistics in this GEMM's epilogue
+  std::shared_ptr<GnPart> gn_share;   // sub-pixel phases 1..3 add to the partial buffer phase 0 created
+  long long gn_rows_per_image = 0;    // linear(): rows per image of the flattened token matrix (0: spatial conv)
 };
 
 struct WT {                      // raw fp32 tensor of the state dict, on device
@@ -164,6 +176,9 @@ class Engine {
   void forward(const IO& io, int B, int H, int W, int direction, int text_batch, cudaStream_t st);
   // cross-attention K / V^T of the prompt, computed once per prompt (i2it_set_text) instead of once per forward
   void set_text(const void* text, int text_batch, cudaStream_t st);
+  // CLIP text tower: tokens [batch, 77] int32 -> last_hidden_state [batch, 77, hidden] in the handle dtype
+  void encode_text(const int* tokens, int batch, void* out, cudaStream_t st);
+  bool has_text_encoder() const { return has("text_encoder.text_model.embeddings.token_embedding.weight"); }
   Plan* last_plan() const { return last_plan_; }
   void read_stage(const std::string& name, float* dst, size_t dst_elems, int dims[4]);
 
@@ -171,9 +186,9 @@ class Engine {
   Act alloc_act(Plan& P, int N, int H, int W, int C, int ld = 0, bool zero_persistent = false);
   std::shared_ptr<void> alloc_raw(Plan& P, size_t bytes);
   Act conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o);
-  Act linear(Plan& P, const Act& x, const PW& w, const Act* res = nullptr, int act = TG_ACT_NONE);
+  Act linear(Plan& P, const Act& x, const PW& w, const Act* res = nullptr, int act = TG_ACT_NONE, bool gn_out = false);
   Act group_norm(Plan& P, const Act& x, const NormW& nw, float eps, bool silu);
-  Act layer_norm(Plan& P, const Act& x, const NormW& nw);
+  Act layer_norm(Plan& P, const Act& x, const NormW& nw, bool to_io_out = false);
   Act upsample2x(Plan& P, const Act& x);
   void copy_channels(Plan& P, const Act& src, const Act& dst_slice);
   // V^T[b] = Wv X[b]^T (+ row bias): returns [B][C][ldv] as an Act with N=B,H=1,W=C,ld=ldv (C field = Ntok)
@@ -181,7 +196,8 @@ class Engine {
   // attention core on projected operands; q/k are column slices of token matrices; returns [B*Nq, heads*d]
   Act attention(Plan& P, const Act& q, const Act& k, const Act& vt, int B, int Nq, int Nk, int heads, int d,
                 int kv_batch);
-  Act flash_attention(Plan& P, const Act& q, const Act& k, const Act& vt, int B, int Nq, int Nk, int heads, int kv_batch);
+  Act flash_attention(Plan& P, const Act& q, const Act& k, const Act& vt, int B, int Nq, int Nk, int heads, int kv_batch,
+                      bool causal = false);
   bool use_flash = true;
 
   // ---- weights ----
@@ -193,7 +209,7 @@ class Engine {
   PW prep_im2col3(const std::string& name);
   PW prep_identity(int n);                                          // [n][n] identity as a 1x1 'weight'
   PW prep_subpixel(const std::string& name);                       // 16 pre-summed 2x2 taps for upsample2x+conv3x3
-  Act conv_up2x(Plan& P, const Act& x, const PW& wsub, const Act* x2, const PW* w2);                        // 3x3 conv over 3 channels as a K=32 single-tap GEMM
+  Act conv_up2x(Plan& P, const Act& x, const PW& wsub, const Act* x2, const PW* w2, bool gn_out = false);                        // 3x3 conv over 3 channels as a K=32 single-tap GEMM
   NormW norm(const std::string& name);
   const float* temb_bias(const std::string& resnet_prefix);          // time_emb_proj(silu(emb)) at t=999
   void free_prepared();
@@ -206,10 +222,11 @@ class Engine {
   void build_text_kv(struct TextKV& T);
   std::vector<std::string> xformer_prefixes() const;
   void build_vae_decoder(Plan& P, const std::string& vp, const Act& dec_in, std::vector<Act>& skips);
-  Act vae_resnet(Plan& P, const std::string& p, const Act& x, const Act* skip = nullptr, const PW* skip_w = nullptr);
+  Act vae_resnet(Plan& P, const std::string& p, const Act& x, const Act* skip = nullptr, const PW* skip_w = nullptr,
+                 bool gn_next = true);
   Act vae_attn(Plan& P, const std::string& p, const Act& x);
-  Act unet_resnet(Plan& P, const std::string& p, const Act& x);
-  Act unet_xformer(Plan& P, const std::string& p, const Act& x, int heads, int text_batch);
+  Act unet_resnet(Plan& P, const std::string& p, const Act& x, bool gn_next = false);
+  Act unet_xformer(Plan& P, const std::string& p, const Act& x, int heads, int text_batch, bool gn_next = false);
   void mark(Plan& P, const std::string& name, const Act& a) { if (cfg.keep_stages) P.stages[name] = a; }
 
   template <typename F> void add_op(Plan& P, F&& f, const char* kind = "misc", double flops = 0, double bytes = 0,
@@ -222,11 +239,12 @@ class Engine {
   void launch_gemm(Plan& P, const TmapSpec& sa, TmapSpec sb, const TapGemmParams& p, bool out_from_io, const char* kind,
                    double k_valid, double bytes, const TmapSpec* sa2 = nullptr, const TmapSpec* sb2 = nullptr,
                    const TmapSpec* shalo = nullptr);
-  bool use_pair = true, use_halo = true, use_idres = true, use_pdl = false, trace_on = false, use_ostage = true;
+  bool use_pair = true, use_halo = true, use_idres = true, use_pdl = false, trace_on = false, use_tmaout = true, use_gnepi = true;
+  bool tma_eligible(const TapGemmParams& p, bool out_from_io) const;
   long long pair_min_tiles = 296;   // CTA-pair kernel from two waves of tiles upwards (tunable: I2IT_PAIR_MIN_TILES)
   std::string profile_json(int reps, cudaStream_t st);
   void dump_trace(Plan& P, cudaStream_t st);
-  int pick_bn(long long m_tiles, int N, bool even32) const;
+  int pick_bn(long long m_tiles, int N, int step) const;   // step 64 / 128: BN restricted to multiples (TMA-store rounds)
 
   int* d_err = nullptr;      // device alias of a mapped host word written by the tapgemm watchdog
   int* err_host_ = nullptr;
@@ -251,6 +269,7 @@ class Engine {
   void push_bias_job(float* out, const float* b, const float* add, int cout, int row_off, int half, float c0 = 1.f,
                      const float* b1 = nullptr, float c1 = 0.f);
   std::map<int, std::unique_ptr<struct TextKV>> textkv_;   // by text_batch
+  std::map<int, std::unique_ptr<Plan>> textenc_;            // CLIP text tower plans, by batch
   std::map<std::vector<int>, std::unique_ptr<Plan>> plans_;
   Plan* last_plan_ = nullptr;
   Act text_;                     // staged text embedding while a UNet plan is being built

@@ -30,6 +30,7 @@ struct FlashParams {
   void* out;                                // [B*Nq, ldo] tokens, head h at columns [64h, 64h+64)
   long long ldo;
   uint32_t idesc;                           // M=128, N=64 (both GEMMs)
+  int causal;                               // 1: key j attends only to queries i >= j (CLIP text tower); KV tiles past the diagonal are skipped
   int* err;
 };
 
@@ -76,7 +77,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const int qt = blockIdx.x % p.q_tiles;
   const int h = (blockIdx.x / p.q_tiles) % p.heads;
   const int b = blockIdx.x / (p.q_tiles * p.heads);
-  const int nkv = (p.Nk + FA_BN - 1) / FA_BN;
+  int nkv = (p.Nk + FA_BN - 1) / FA_BN;
+  if (p.causal) nkv = min(nkv, (qt * FA_BM + FA_BM + FA_BN - 1) / FA_BN);   // same value in all three roles
 
   if (warp == 4 && lane == 0) {
     mbar_init(q_full, 1);
@@ -166,7 +168,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc_fence_after();
       const uint32_t tS = tS0 + 64 * (j & 1);
       const int kbase = j * FA_BN;
-      const bool ragged = (kbase + FA_BN > p.Nk);          // only the last KV tile; warp-uniform
+      const int qpos = qt * FA_BM + row;
+      // element-wise masking only where needed (warp-uniform): the last KV tile, or causal tiles that reach this warp's diagonal
+      const bool ragged = (kbase + FA_BN > p.Nk) || (p.causal && kbase + FA_BN - 1 > qt * FA_BM + warp * 32);
+      const int klim = p.causal ? min(p.Nk, qpos + 1) : p.Nk;   // keys [0, klim) are visible to this row
       const float sc = p.scale_log2e;
       // pass 1: row max of the RAW logits (scale > 0 keeps the order; one FMNMX per element)
       float mx = -INFINITY;
@@ -178,7 +183,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         if (ragged) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (kbase + half * 32 + i < p.Nk) mx = fmaxf(mx, __uint_as_float(raw[i]));
+            if (kbase + half * 32 + i < klim) mx = fmaxf(mx, __uint_as_float(raw[i]));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
@@ -213,8 +218,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int k0 = kbase + half * 32 + 2 * i;
-            const float p0 = (k0 < p.Nk) ? fast_exp2(fmaf(__uint_as_float(raw[2 * i]), sc, neg_ms)) : 0.f;
-            const float p1 = (k0 + 1 < p.Nk) ? fast_exp2(fmaf(__uint_as_float(raw[2 * i + 1]), sc, neg_ms)) : 0.f;
+            const float p0 = (k0 < klim) ? fast_exp2(fmaf(__uint_as_float(raw[2 * i]), sc, neg_ms)) : 0.f;
+            const float p1 = (k0 + 1 < klim) ? fast_exp2(fmaf(__uint_as_float(raw[2 * i + 1]), sc, neg_ms)) : 0.f;
             psum += p0 + p1;
             pk[i] = Elem<T>::pack(p0, p1);
           }

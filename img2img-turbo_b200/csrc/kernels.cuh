@@ -96,6 +96,39 @@ static __global__ void gn_finalize_kernel(const float* __restrict__ partial, int
   }
 }
 
+// Finalize from the partials a producing GEMM's epilogue wrote (TapGemmParams::gn_part): block (g, n) reduces group g of image n
+// over [phases][slots][entries-per-group] in a fixed order (double accumulation, reproducible, no atomics).
+static __global__ void gn_finalize_part_kernel(const float* __restrict__ part, int phases, int images, int slots, int per_row,
+                                               int epg, double inv_count, float eps, float* __restrict__ stats) {
+  pdl_sync();
+  __shared__ double2 red[256];
+  const int g = blockIdx.x, n = blockIdx.y;
+  double a = 0.0, b = 0.0;
+  const long long items = static_cast<long long>(slots) * epg;
+  for (int ph = 0; ph < phases; ++ph) {
+    const float2* base = reinterpret_cast<const float2*>(part) + (static_cast<long long>(ph) * images + n) * slots * per_row + g * epg;
+    for (long long i = threadIdx.x; i < items; i += 256) {
+      const long long sl = i / epg;
+      const int e = static_cast<int>(i - sl * epg);
+      const float2 v = base[sl * per_row + e];
+      a += static_cast<double>(v.x); b += static_cast<double>(v.y);
+    }
+  }
+  red[threadIdx.x] = make_double2(a, b);
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { red[threadIdx.x].x += red[threadIdx.x + o].x; red[threadIdx.x].y += red[threadIdx.x + o].y; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double mean = red[0].x * inv_count;
+    double var = red[0].y * inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[(n * 32 + g) * 2] = static_cast<float>(mean);
+    stats[(n * 32 + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+}
+
 template <typename T>
 __global__ void gn_apply_kernel(const T* __restrict__ x, long long ximg, int ldx, T* __restrict__ y, long long yimg,
                                 int ldy, int C, int HW, int cg, int pix_per_cta, const float* __restrict__ stats,
@@ -250,6 +283,29 @@ __global__ void softmax_kernel(const float* __restrict__ s, long long lds, T* __
     const int c = tr + i * TPR;
     if (c < nk_pad) o[c] = Elem<T>::from_f(c < nk ? v[i] * inv : 0.f);
   }
+}
+
+// =============================================================================================
+// CLIP text embeddings: out[b, t, :] = token_embedding[ids[b, t]] + position_embedding[t]   (fp32 add, one rounding)
+// (transformers models/clip/modeling_clip.py CLIPTextEmbeddings.forward; reference call /root/reference/src/pix2pix_turbo.py:190-196)
+// =============================================================================================
+template <typename T>
+__global__ void clip_embed_kernel(const int* __restrict__ ids, const float* __restrict__ tok, const float* __restrict__ pos,
+                                  T* __restrict__ out, int C, int ntok, int vocab, long long total /* rows * C/8 */) {
+  pdl_sync();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int vecs = C >> 3;
+  const long long r = i / vecs;
+  const int v = static_cast<int>(i % vecs);
+  const int t = static_cast<int>(r % ntok);
+  int id = ids[r];
+  id = min(max(id, 0), vocab - 1);
+  const float4* a = reinterpret_cast<const float4*>(tok + static_cast<long long>(id) * C + v * 8);
+  const float4* b = reinterpret_cast<const float4*>(pos + static_cast<long long>(t) * C + v * 8);
+  const float4 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
+  st16(out + r * C + v * 8, make_uint4(Elem<T>::pack(a0.x + b0.x, a0.y + b0.y), Elem<T>::pack(a0.z + b0.z, a0.w + b0.w),
+                                       Elem<T>::pack(a1.x + b1.x, a1.y + b1.y), Elem<T>::pack(a1.z + b1.z, a1.w + b1.w)));
 }
 
 // =============================================================================================

@@ -20,11 +20,13 @@ static inline int ceil_div_i(long long a, long long b) { return static_cast<int>
   } while (0)
 
 // ------------------------------------------------------------------------------------------ VAE
-Act Engine::vae_resnet(Plan& P, const std::string& p, const Act& x, const Act* skip, const PW* skip_w) {
+Act Engine::vae_resnet(Plan& P, const std::string& p, const Act& x, const Act* skip, const PW* skip_w, bool gn_next) {
   Act h = group_norm(P, x, norm(p + ".norm1"), 1e-6f, true);
-  h = conv(P, h, prep(p + ".conv1", {p + ".conv1"}), ConvOpts());
+  ConvOpts o1; o1.gn_out = true;                     // conv1 feeds norm2: its epilogue takes the GroupNorm statistics
+  h = conv(P, h, prep(p + ".conv1", {p + ".conv1"}), o1);
   h = group_norm(P, h, norm(p + ".norm2"), 1e-6f, true);
   ConvOpts o;
+  o.gn_out = gn_next;                                // the block's output feeds another GroupNorm (norm1 / attention / conv_norm_out)
   if (has(p + ".conv_shortcut.weight")) {
     // x + conv2(h) with a 1x1 shortcut: the shortcut is one more K-slab of the SAME GEMM (second A tensor), its bias is
     // pre-added to conv2's, so there is no separate launch and no residual read
@@ -47,7 +49,7 @@ Act Engine::vae_attn(Plan& P, const std::string& p, const Act& x) {
   Act vt = vt_proj(P, t, B, N, prep(p + ".to_v", {p + ".to_v"}));
   Act a = attention(P, qk.slice(0, C), qk.slice(C, C), vt, B, N, N, 1, C, B);
   a.N = x.N; a.H = x.H; a.W = x.W;
-  return linear(P, a, prep(p + ".to_out.0", {p + ".to_out.0"}), &x);
+  return linear(P, a, prep(p + ".to_out.0", {p + ".to_out.0"}), &x, TG_ACT_NONE, true);   // -> mid_block.resnets.1.norm1
 }
 
 Act Engine::build_vae_encoder(Plan& P, const std::string& vp, int B, int H, int W, std::vector<Act>& skips, bool u8_in) {
@@ -72,15 +74,17 @@ Act Engine::build_vae_encoder(Plan& P, const std::string& vp, int B, int H, int 
       }, "pack_im2col", 0, 2.0 * total * (3 + 32));
     }
   }
-  ConvOpts oin; oin.ksize = 1;
+  ConvOpts oin; oin.ksize = 1; oin.gn_out = true;
   Act s = conv(P, xcol, prep_im2col3(e + ".conv_in"), oin);
   xcol = Act();
   for (int i = 0; i < 4; ++i) {
     skips.push_back(s);                                   // model.py:18-20: the INPUT of each down block
     mark(P, "skip" + std::to_string(i), s);
-    for (int j = 0; j < 2; ++j) s = vae_resnet(P, e + ".down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), s);
+    for (int j = 0; j < 2; ++j)      // the last resnet before a downsampler feeds a conv, not a GroupNorm
+      s = vae_resnet(P, e + ".down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), s, nullptr, nullptr,
+                     !(j == 1 && i < 3));
     if (i < 3) {
-      ConvOpts o; o.stride = 2; o.asym = true;
+      ConvOpts o; o.stride = 2; o.asym = true; o.gn_out = true;
       const std::string d = e + ".down_blocks." + std::to_string(i) + ".downsamplers.0.conv";
       s = conv(P, s, prep(d, {d}), o);
     }
@@ -117,7 +121,7 @@ void Engine::build_vae_decoder(Plan& P, const std::string& vp, const Act& dec_in
   const std::string d = vp + "decoder";
   ConvOpts o1; o1.ksize = 1;
   Act s = conv(P, dec_in, prep(vp + "post_quant_conv", {vp + "post_quant_conv"}), o1);
-  s = conv(P, s, prep(d + ".conv_in", {d + ".conv_in"}), ConvOpts());
+  { ConvOpts oc; oc.gn_out = true; s = conv(P, s, prep(d + ".conv_in", {d + ".conv_in"}), oc); }
   // `sample = sample + skip_conv_i(skip_i * gamma)` (src/model.py:40-42) is folded into whichever conv PRODUCES `sample`
   // for up-block i: mid_block.resnets.1.conv2 for i = 0, the previous block's upsampler conv for i >= 1.  gamma is folded
   // into the bias-free 1x1 weights.
@@ -131,13 +135,15 @@ void Engine::build_vae_decoder(Plan& P, const std::string& vp, const Act& dec_in
   }
   mark(P, "dec_mid", s);
   for (int i = 0; i < 4; ++i) {
-    for (int j = 0; j < 3; ++j) s = vae_resnet(P, d + ".up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), s);
+    for (int j = 0; j < 3; ++j)      // resnets.2 feeds the upsampler conv (i < 3) or conv_norm_out (i == 3)
+      s = vae_resnet(P, d + ".up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), s, nullptr, nullptr,
+                     !(j == 2 && i < 3));
     if (i < 3) {
       // Upsample2D: nearest-2x + conv3x3, as four parity-phase 2x2 convs on the low-res tensor (2.25x fewer FLOPs, the
       // upsampled tensor never exists); the next block's skip conv rides along as a second source at output resolution
       const std::string u = d + ".up_blocks." + std::to_string(i) + ".upsamplers.0.conv";
       PW wn = skip_w(i + 1);
-      s = conv_up2x(P, s, prep_subpixel(u), &skips[2 - i], &wn);
+      s = conv_up2x(P, s, prep_subpixel(u), &skips[2 - i], &wn, true);
       skips[2 - i] = Act();
     }
     mark(P, "dec_up" + std::to_string(i), s);
@@ -152,12 +158,14 @@ void Engine::build_vae_decoder(Plan& P, const std::string& vp, const Act& dec_in
 }
 
 // ------------------------------------------------------------------------------------------ UNet
-Act Engine::unet_resnet(Plan& P, const std::string& p, const Act& x) {
+Act Engine::unet_resnet(Plan& P, const std::string& p, const Act& x, bool gn_next) {
   Act h = group_norm(P, x, norm(p + ".norm1"), 1e-5f, true);
   // t == 999 always: time_emb_proj(silu(emb)) is a per-channel constant -> part of conv1's bias
-  h = conv(P, h, prep(p + ".conv1", {p + ".conv1"}, false, 1.f, temb_bias(p)), ConvOpts());
+  ConvOpts o1; o1.gn_out = true;
+  h = conv(P, h, prep(p + ".conv1", {p + ".conv1"}, false, 1.f, temb_bias(p)), o1);
   h = group_norm(P, h, norm(p + ".norm2"), 1e-5f, true);
   ConvOpts o;
+  o.gn_out = gn_next;
   if (has(p + ".conv_shortcut.weight")) {
     PW wsc = prep(p + ".conv_shortcut", {p + ".conv_shortcut"});
     PW w2 = prep(p + ".conv2+sc", {p + ".conv2"}, false, 1.f, raw(p + ".conv_shortcut", "bias").d);
@@ -168,7 +176,7 @@ Act Engine::unet_resnet(Plan& P, const std::string& p, const Act& x) {
   return conv(P, h, prep(p + ".conv2", {p + ".conv2"}), o);
 }
 
-Act Engine::unet_xformer(Plan& P, const std::string& p, const Act& x, int heads, int text_batch) {
+Act Engine::unet_xformer(Plan& P, const std::string& p, const Act& x, int heads, int text_batch, bool gn_next) {
   const int C = x.C, B = x.N, N = x.H * x.W, d = C / heads;
   const std::string b = p + ".transformer_blocks.0";
   Act t = group_norm(P, x, norm(p + ".norm"), 1e-6f, false);
@@ -202,7 +210,7 @@ Act Engine::unet_xformer(Plan& P, const std::string& p, const Act& x, int heads,
     Act g = linear(P, n, prep(b + ".ff.net.0.proj", {b + ".ff.net.0.proj"}, true), nullptr, TG_ACT_GEGLU);
     t = linear(P, g, prep(b + ".ff.net.2", {b + ".ff.net.2"}), &t);
   }
-  return linear(P, t, prep(p + ".proj_out", {p + ".proj_out"}), &x);
+  return linear(P, t, prep(p + ".proj_out", {p + ".proj_out"}), &x, TG_ACT_NONE, gn_next);
 }
 
 // every transformer block of the UNet, in execution-independent fixed order (the cross-attention K/V^T cache is keyed by it)
@@ -263,27 +271,31 @@ Act Engine::build_unet(Plan& P, const Act& z, int text_batch, bool text_cached) 
   }
   Act s;
   if (has(u + ".conv_in.conv_in_pretrained.weight")) {
-    s = conv(P, z, prep_twin(u + ".conv_in.conv_in_pretrained", u + ".conv_in.conv_in_curr", twin_r_), ConvOpts());
+    ConvOpts oc; oc.gn_out = true;
+    s = conv(P, z, prep_twin(u + ".conv_in.conv_in_pretrained", u + ".conv_in.conv_in_curr", twin_r_), oc);
   } else {
-    s = conv(P, z, prep(u + ".conv_in", {u + ".conv_in"}), ConvOpts());
+    ConvOpts oc; oc.gn_out = true;
+    s = conv(P, z, prep(u + ".conv_in", {u + ".conv_in"}), oc);
   }
   std::vector<Act> res{s};
   for (int i = 0; i < 4; ++i) {
     const std::string blk = u + ".down_blocks." + std::to_string(i);
     for (int j = 0; j < 2; ++j) {
-      s = unet_resnet(P, blk + ".resnets." + std::to_string(j), s);
-      if (i < 3) s = unet_xformer(P, blk + ".attentions." + std::to_string(j), s, heads[i], text_batch);
+      // who consumes the output decides whether the producing GEMM takes GroupNorm statistics: the transformer's GroupNorm
+      // (i < 3), the next resnet's norm1 (j == 0, or the mid block after the last down block) — not the downsampler conv
+      s = unet_resnet(P, blk + ".resnets." + std::to_string(j), s, true);
+      if (i < 3) s = unet_xformer(P, blk + ".attentions." + std::to_string(j), s, heads[i], text_batch, j == 0);
       res.push_back(s);
     }
     if (i < 3) {
-      ConvOpts o; o.stride = 2;
+      ConvOpts o; o.stride = 2; o.gn_out = true;
       s = conv(P, s, prep(blk + ".downsamplers.0.conv", {blk + ".downsamplers.0.conv"}), o);
       res.push_back(s);
     }
   }
-  s = unet_resnet(P, u + ".mid_block.resnets.0", s);
-  s = unet_xformer(P, u + ".mid_block.attentions.0", s, heads[3], text_batch);
-  s = unet_resnet(P, u + ".mid_block.resnets.1", s);
+  s = unet_resnet(P, u + ".mid_block.resnets.0", s, true);
+  s = unet_xformer(P, u + ".mid_block.attentions.0", s, heads[3], text_batch, true);
+  s = unet_resnet(P, u + ".mid_block.resnets.1", s, false);          // -> concat (GroupNorm over the concatenation)
   mark(P, "unet_mid", s);
   for (int i = 0; i < 4; ++i) {
     const std::string blk = u + ".up_blocks." + std::to_string(i);
@@ -295,8 +307,9 @@ Act Engine::build_unet(Plan& P, const Act& z, int text_batch, bool text_cached) 
       copy_channels(P, s, cat.slice(0, s.C));
       copy_channels(P, skip, cat.slice(s.C, skip.C));
       skip = Act();
-      s = unet_resnet(P, blk + ".resnets." + std::to_string(j), cat);
-      if (i > 0) s = unet_xformer(P, blk + ".attentions." + std::to_string(j), s, hcount, text_batch);
+      const bool last = (i == 3 && j == 2);                            // the very last block feeds conv_norm_out directly
+      s = unet_resnet(P, blk + ".resnets." + std::to_string(j), cat, i > 0);
+      if (i > 0) s = unet_xformer(P, blk + ".attentions." + std::to_string(j), s, hcount, text_batch, last);
     }
     if (i < 3) {
       s = upsample2x(P, s);

@@ -35,22 +35,26 @@ constexpr int TG_B_STAGE = 256 * TG_BK * 2;      // 32 KiB (BN <= 256)
 constexpr int TG_EPI_WARPS = I2IT_EPI_WARPS;   // TG_EPI_GROUPS warps per TMEM lane quarter: they take the 32-column rounds in turn
 constexpr int TG_EPI_GROUPS = TG_EPI_WARPS / 4;
 constexpr int TG_EPI_RPW = 8 / TG_EPI_GROUPS;      // rounds per warp at BN = 256
-static_assert(TG_EPI_WARPS == 8 || TG_EPI_WARPS == 16, "epilogue warps: 8 or 16");
+static_assert(TG_EPI_WARPS == 8, "epilogue warps: 8 (the 16-warp experiment of round 1 does not fit next to the 4 KB store boxes)");
 constexpr int TG_BAR_BYTES = 256;
 constexpr int TG_BIAS_BYTES = 2 * 256 * 4;       // per-tile bias slice, double-buffered like the accumulators
-// epilogue store staging: each epilogue warp owns a 32-row x 64-byte tile (XOR-swizzled 16-byte chunks).  A thread holds one
-// accumulator ROW, so direct stores touch 32 different lines per instruction (measured: ~6000 cycles per 128x160 tile, the
-// limiter of every small-K GEMM); through the tile a store instruction writes 8 rows x 64 contiguous bytes instead.
-constexpr int TG_OSTG_WARP = 32 * 64;
+// Epilogue store staging: each epilogue warp owns ONE TMA box = 32 rows x 64 output columns (128-byte rows, SWIZZLE_128B: the
+// 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)).  A thread holds one accumulator ROW, so direct stores touch 32
+// different lines per instruction (r01 trace: ~6000 cycles of LSU transactions per 128x160 tile, the limiter of every
+// K <= ~1152 GEMM).  Through the box the thread writes its row with conflict-free st.shared.v4 and ONE elected lane hands the
+// 4 KB box to the TMA unit (cp.async.bulk.tensor...global.shared::cta = UTMASTG), which writes full lines and clips ragged edges.
+// The residual takes the same road in reverse: coalesced 16-byte global loads (4 rows x 128 B per instruction), transposed
+// through the box, added in place.
+constexpr int TG_OSTG_WARP = 32 * 128;
 constexpr int TG_OSTG_BYTES = TG_EPI_WARPS * TG_OSTG_WARP;
-// manual 1024-byte alignment slack of the dynamic smem base.  The 16-warp build is 256 B over the 227 KB limit with a full 1 KB
-// of slack, so it budgets 768 B and the kernels trap (error word) if the runtime base needs more (it is 1 KB aligned in practice).
-constexpr int TG_ALIGN_PAD = (TG_EPI_WARPS == 16) ? 768 : 1024;
+// manual 1024-byte alignment slack of the dynamic smem base: 768 B are budgeted (a full 1 KB would put the CTA 256 B over the
+// 227 KB limit) and the kernels trap with an error word if the runtime base needs more (it is 1 KB aligned in practice).
+constexpr int TG_ALIGN_PAD = 768;
 constexpr int TG_SMEM = TG_STAGES * (TG_A_STAGE + TG_B_STAGE) + TG_BAR_BYTES + TG_BIAS_BYTES + TG_OSTG_BYTES + TG_ALIGN_PAD;
 constexpr int TG_THREADS = (TG_EPI_WARPS + 2) * 32;   // + TMA producer warp + MMA issuer warp
 constexpr int TG_ACC_COLS = 256;       // TMEM columns per accumulator stage
 
-enum TgAct : int { TG_ACT_NONE = 0, TG_ACT_CLAMP1 = 1, TG_ACT_GEGLU = 2 };
+enum TgAct : int { TG_ACT_NONE = 0, TG_ACT_CLAMP1 = 1, TG_ACT_GEGLU = 2, TG_ACT_GELU = 3, TG_ACT_QUICKGELU = 4 };   // 3, 4: CLIP MLP
 enum TgBias : int { TG_BIAS_NONE = 0, TG_BIAS_COL = 1, TG_BIAS_ROW = 2 };
 
 struct TapGemmParams {
@@ -84,7 +88,11 @@ struct TapGemmParams {
   float alpha;
   int act;
   int* err;               // device error word (watchdog)
-  int ostage;             // 1: stage 16-bit row-major output rounds through smem for coalesced stores (I2IT_NO_OSTG=1 -> 0)
+  int tma_out;            // 1: 64-column rounds are staged in smem and stored by TMA (I2IT_NO_TMAOUT=1 -> 0: per-thread stores)
+  // GroupNorm statistics of the OUTPUT tensor, taken from the staged (rounded) tile: per 32-row slot and per `gn_red` columns,
+  // (sum, sum of squares) -> gn_part[(slot0 + m_tile*4 + quarter) * (N/gn_red) + col/gn_red][2]; nullptr = off
+  float* gn_part;
+  int gn_red, gn_slot0, gn_mtiles;   // gn_mtiles: m-tiles of the launch (the pair kernel's odd tail tile has no slot)
   unsigned long long* trace;   // optional (I2IT_TRACE=1): 16 %clock64 stamps per CTA at the phase boundaries, else nullptr
 };
 
@@ -138,6 +146,17 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// TMA store of one box from shared memory (async proxy): the writer threads fence (fence.proxy.async) and sync first
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // one lane of a fully converged warp (warp-uniform control flow keeps descriptors/addresses in uniform registers)
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -221,7 +240,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int til
 template <typename T>
 __device__ __forceinline__ void epilogue_chunk(const TapGemmParams& p, const uint32_t (&raw)[16], int col0, long long obase,
                                                long long rbase, float rbias, const float* sbias, bool rfast, const uint4& r0,
-                                               const uint4& r1, uint32_t stg = 0u, int stg_chunk = 0, int stg_row = 0) {
+                                               const uint4& r1) {
   float v[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
@@ -244,12 +263,7 @@ __device__ __forceinline__ void epilogue_chunk(const TapGemmParams& p, const uin
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] += Elem<T>::to_f(rptr[i]);
     }
-    if (stg) {                                    // staged round (caller checked: full columns, aligned rows)
-      uint4 u;
-      u.x = Elem<T>::pack(o[0], o[1]); u.y = Elem<T>::pack(o[2], o[3]);
-      u.z = Elem<T>::pack(o[4], o[5]); u.w = Elem<T>::pack(o[6], o[7]);
-      sts16(stg + ((stg_chunk ^ (stg_row >> 1)) & 3) * 16, u);
-    } else if (full && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0)) {
+    if (full && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0)) {
       uint4 u;
       u.x = Elem<T>::pack(o[0], o[1]); u.y = Elem<T>::pack(o[2], o[3]);
       u.z = Elem<T>::pack(o[4], o[5]); u.w = Elem<T>::pack(o[6], o[7]);
@@ -259,6 +273,13 @@ __device__ __forceinline__ void epilogue_chunk(const TapGemmParams& p, const uin
       for (int i = 0; i < 8; ++i) if (col0 + 2 * i + 1 < p.N) optr[i] = Elem<T>::from_f(o[i]);
     }
     return;
+  }
+  if (p.act == TG_ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = gelu_erf_f(v[i]);
+  } else if (p.act == TG_ACT_QUICKGELU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = quick_gelu_f(v[i]);
   }
   if (p.res) {
     if (rfast) {
@@ -290,15 +311,7 @@ __device__ __forceinline__ void epilogue_chunk(const TapGemmParams& p, const uin
     }
   } else {
     T* optr = reinterpret_cast<T*>(p.out) + obase + col0 * p.ocol;
-    if (stg) {
-      uint4 u0, u1;
-      u0.x = Elem<T>::pack(v[0], v[1]);   u0.y = Elem<T>::pack(v[2], v[3]);
-      u0.z = Elem<T>::pack(v[4], v[5]);   u0.w = Elem<T>::pack(v[6], v[7]);
-      u1.x = Elem<T>::pack(v[8], v[9]);   u1.y = Elem<T>::pack(v[10], v[11]);
-      u1.z = Elem<T>::pack(v[12], v[13]); u1.w = Elem<T>::pack(v[14], v[15]);
-      sts16(stg + (((2 * stg_chunk) ^ (stg_row >> 1)) & 3) * 16, u0);
-      sts16(stg + (((2 * stg_chunk + 1) ^ (stg_row >> 1)) & 3) * 16, u1);
-    } else if (full && p.ocol == 1 && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0)) {
+    if (full && p.ocol == 1 && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0)) {
       uint4 u0, u1;
       u0.x = Elem<T>::pack(v[0], v[1]);   u0.y = Elem<T>::pack(v[2], v[3]);
       u0.z = Elem<T>::pack(v[4], v[5]);   u0.w = Elem<T>::pack(v[6], v[7]);
@@ -313,16 +326,19 @@ __device__ __forceinline__ void epilogue_chunk(const TapGemmParams& p, const uin
   }
 }
 
-// The whole epilogue of one output tile for one thread (= one accumulator row): bias slice staged in smem, residual
-// prefetched a round ahead, accumulator pulled from TMEM 32 columns at a time, single rounding, 64-byte stores.
-// Shared by the 1-CTA and the 2-CTA kernels.  Caller signals tmem_empty afterwards.
+// The whole epilogue of one output tile for one thread (= one accumulator row).  Shared by the 1-CTA and the 2-CTA kernels.
+// Caller signals tmem_empty afterwards.  Two paths, chosen per launch on the host:
+//   * tma_out: 64-column rounds -> this warp's swizzled 4 KB box in smem -> one TMA store per round (see TG_OSTG_WARP);
+//     the residual is fetched with coalesced loads before the accumulator wait and added from the box; optional GroupNorm
+//     statistics of the rounded output come from the box as well;
+//   * direct: each thread stores its own row (fp32 logits, NCHW image, row-bias V^T, channel counts that are not multiples of 64).
 template <typename T>
-__device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const TileCoord& c, int row, int warp, int j1, int j2,
-                                              int j3, int j4, int acc, int aphase, uint32_t tmem_base, float* s_bias,
-                                              uint32_t tfull_bar_addr, bool stamp = false) {
+__device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const CUtensorMap* tmO, const TileCoord& c, int m_tile,
+                                              int row, int warp, int j1, int j2, int j3, int j4, int acc, int aphase,
+                                              uint32_t tmem_base, float* s_bias, uint32_t ostg_base, uint32_t tfull_bar_addr,
+                                              bool stamp = false) {
   const int lane = threadIdx.x & 31;
-  const uint32_t ostg_warp = smem_u32(s_bias) + TG_BIAS_BYTES + warp * TG_OSTG_WARP;   // this warp's staging tile
-  const uint32_t ostg_row = ostg_warp + lane * 64;
+  const uint32_t ostg_warp = ostg_base + warp * TG_OSTG_WARP;   // this warp's store box (1024-byte aligned)
   const int grp = warp >> 2;                     // which of the two warps sharing this TMEM lane quarter
   const int g1 = c.t[0] * p.box[0] + j1, g2 = c.t[1] * p.box[1] + j2, g3 = c.t[2] * p.box[2] + j3,
             g4 = c.t[3] * p.box[3] + j4;
@@ -340,12 +356,166 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const Tile
   }
   asm volatile("bar.sync 1, %0;" ::"n"(TG_EPI_WARPS * 32) : "memory");   // the epilogue warps only
   if (stamp) tg_stamp(p, 7);
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + acc * TG_ACC_COLS;
+  const bool geglu = p.act == TG_ACT_GEGLU;
 
+  if (p.tma_out) {
+    // ================= TMA-store path: rounds of 64 OUTPUT columns (64 accumulator columns, 128 for GEGLU) =================
+    const int acols = geglu ? 128 : 64;                       // accumulator columns per round
+    const int nrounds = p.BN / acols;                         // host guarantees BN % acols == 0 and N % acols == 0
+    const bool res_on = p.res != nullptr && !geglu;
+    // Residual prefetch: independent of the accumulator, so it is requested BEFORE the accumulator wait and its latency
+    // overlaps the mainloop.  Instruction i loads rows 4i..4i+3 of the warp's 32 (8 lanes x 16 B = one full 128-byte row
+    // segment each) -> 4 fully used lines per instruction instead of 32 half-used sectors.
+    uint4 rq[8];
+    const int lrow = lane >> 3, lch = lane & 7;
+    auto load_res = [&](int r) {                             // this warp's residual box of round r -> registers
+      const int colg = n0 + 64 * r;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int src_row = 4 * i + lrow;
+        const long long rb = __shfl_sync(0xffffffffu, rbase, src_row);
+        const int ok = __shfl_sync(0xffffffffu, static_cast<int>(row_ok), src_row);
+        rq[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (ok && r < nrounds && colg < p.N)
+          rq[i] = ld_nc16(reinterpret_cast<const T*>(p.res) + rb + colg + lch * 8);
+      }
+    };
+    if (res_on) load_res(grp);
+    mbar_wait(tfull_bar_addr, aphase, p.err, 4);
+    tc_fence_after();
+    if (stamp) tg_stamp(p, 8);
+    const uint32_t my_row = ostg_warp + lane * 128;
+    const int sw = lane & 7;
+#pragma unroll
+    for (int k = 0; k < TG_EPI_RPW / 2; ++k) {
+      const int r = grp + TG_EPI_GROUPS * k;
+      if (r >= nrounds) break;                               // warp-uniform
+      const int c0 = acols * r;                              // accumulator column of this round inside the tile
+      if (n0 + c0 >= p.N) break;                             // whole round beyond N (last n-tile): nothing to store
+      // the previous TMA store out of this box must have finished READING it
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+      if (res_on) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + lrow;
+          sts16(ostg_warp + rr * 128 + ((lch ^ (rr & 7)) << 4), rq[i]);
+        }
+        __syncwarp();
+        if (r + TG_EPI_GROUPS < nrounds) load_res(r + TG_EPI_GROUPS);   // next round's residual: in flight during this round's math
+      }
+      const int nq = geglu ? 4 : 2;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {                          // 32 accumulator columns per step
+        if (q >= nq) break;                                  // warp-uniform
+        uint32_t raw0[16], raw1[16];
+        tc_ld16(taddr + c0 + 32 * q, raw0);
+        tc_ld16(taddr + c0 + 32 * q + 16, raw1);
+        tc_wait_ld();
+        const float* sbq = sb + c0 + 32 * q;
+        if (geglu) {
+          // interleaved accumulator columns (2j, 2j+1) = (h_j, gate_j) -> output column j = h * gelu(gate): 32 -> 16 columns
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t* raw = h ? raw1 : raw0;
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float hv = __uint_as_float(raw[2 * i]) * p.alpha + sbq[16 * h + 2 * i];
+              const float gv = __uint_as_float(raw[2 * i + 1]) * p.alpha + sbq[16 * h + 2 * i + 1];
+              o[i] = hv * gelu_erf_f(gv);
+            }
+            uint4 u;
+            u.x = Elem<T>::pack(o[0], o[1]); u.y = Elem<T>::pack(o[2], o[3]);
+            u.z = Elem<T>::pack(o[4], o[5]); u.w = Elem<T>::pack(o[6], o[7]);
+            sts16(my_row + (((2 * q + h) ^ sw) << 4), u);
+          }
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t* raw = h ? raw1 : raw0;
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
+            if (p.bias_mode == TG_BIAS_COL) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += sbq[16 * h + i];
+            }
+            if (p.act == TG_ACT_GELU) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = gelu_erf_f(v[i]);
+            } else if (p.act == TG_ACT_QUICKGELU) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = quick_gelu_f(v[i]);
+            }
+            const uint32_t a0 = my_row + (((4 * q + 2 * h) ^ sw) << 4), a1 = my_row + (((4 * q + 2 * h + 1) ^ sw) << 4);
+            if (res_on) {
+              const uint4 r0 = lds16(a0), r1 = lds16(a1);
+              const uint32_t ru[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float2 f = Elem<T>::unpack(ru[i]);
+                v[2 * i] += f.x; v[2 * i + 1] += f.y;
+              }
+            }
+            if (p.act == TG_ACT_CLAMP1) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fminf(fmaxf(v[i], -1.0f), 1.0f);
+            }
+            uint4 u0, u1;
+            u0.x = Elem<T>::pack(v[0], v[1]);   u0.y = Elem<T>::pack(v[2], v[3]);
+            u0.z = Elem<T>::pack(v[4], v[5]);   u0.w = Elem<T>::pack(v[6], v[7]);
+            u1.x = Elem<T>::pack(v[8], v[9]);   u1.y = Elem<T>::pack(v[10], v[11]);
+            u1.z = Elem<T>::pack(v[12], v[13]); u1.w = Elem<T>::pack(v[14], v[15]);
+            sts16(a0, u0);
+            sts16(a1, u1);
+          }
+        }
+      }
+      fence_async_smem();                                    // generic-proxy writes -> visible to the TMA unit
+      __syncwarp();
+      const int ocol0 = geglu ? ((n0 + c0) >> 1) : (n0 + c0);
+      if (lane == 0) {                                       // lane 0 holds the box origin: its own row coordinates
+        tma_store_5d(tmO, ostg_warp, ocol0, g1, g2, g3, g4);
+        bulk_commit();
+      }
+      if (p.gn_part) {
+        // GroupNorm statistics of the tensor just produced, from the ROUNDED values in the box (what the next layer's GroupNorm
+        // sees): lane l sums columns 2l, 2l+1 over the warp's 32 rows (conflict-free: a row's 32 words sit in 32 banks), then
+        // gn_red/2 neighbouring lanes are combined by shuffles.  One deterministic store per (slot, column group): no atomics.
+        float s = 0.f, qq = 0.f;
+        const unsigned okmask = __ballot_sync(0xffffffffu, row_ok);
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr) {
+          uint32_t w;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(ostg_warp + rr * 128 + ((((lane >> 2) ^ (rr & 7)) << 4) | ((lane & 3) << 2))));
+          if ((okmask >> rr) & 1u) {
+            const float2 f = Elem<T>::unpack(w);
+            s += f.x + f.y; qq += f.x * f.x + f.y * f.y;
+          }
+        }
+        for (int o = 1; o < (p.gn_red >> 1); o <<= 1) {
+          s += __shfl_xor_sync(0xffffffffu, s, o);
+          qq += __shfl_xor_sync(0xffffffffu, qq, o);
+        }
+        const int lanes_per = p.gn_red >> 1;                 // lanes per output entry (1, 2, 4 or 8)
+        if ((lane & (lanes_per - 1)) == 0 && m_tile < p.gn_mtiles) {   // slots without a valid row still get their zeros
+          const int per_row = (geglu ? (p.N >> 1) : p.N) / p.gn_red;
+          const long long slot = p.gn_slot0 + static_cast<long long>(m_tile) * 4 + (warp & 3);
+          float2* dst = reinterpret_cast<float2*>(p.gn_part) + slot * per_row + (ocol0 + 2 * lane) / p.gn_red;
+          *dst = make_float2(s, qq);
+        }
+      }
+    }
+    return;
+  }
+
+  // ================= direct path =================
   // Residual reads do not depend on the accumulator: this thread's WHOLE residual slice (its row x the 32-column rounds
-  // r = grp, grp+2, ...; <= 256 B) is requested before the accumulator wait, so global-load latency overlaps the mainloop
-  // (one round of lookahead left the epilogue latency-bound: 0.95 ms vs 0.60 ms for the same conv with/without residual).
+  // r = grp, grp+2, ...; <= 256 B) is requested before the accumulator wait, so global-load latency overlaps the mainloop.
   const int nrounds = (p.BN + 31) >> 5;
-  const bool res_on = p.res != nullptr && row_ok && p.rcol == 1 && p.act != TG_ACT_GEGLU;
+  const bool res_on = p.res != nullptr && row_ok && p.rcol == 1 && !geglu;
   uint4 rq[TG_EPI_RPW][4];
   bool fast[TG_EPI_RPW];
 #pragma unroll
@@ -367,7 +537,6 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const Tile
   mbar_wait(tfull_bar_addr, aphase, p.err, 4);
   tc_fence_after();
   if (stamp) tg_stamp(p, 8);
-  const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + acc * TG_ACC_COLS;
 
 #pragma unroll
   for (int i = 0; i < TG_EPI_RPW; ++i) {
@@ -381,31 +550,10 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const Tile
     if (nch == 2) tc_ld16(taddr + c0 + 16, raw1);
     tc_wait_ld();
     const int col0 = n0 + c0;
-    // Staged round (warp-uniform decision): 16-bit contiguous output, every column of the round inside N, every row 16-byte
-    // aligned.  Otherwise (fp32 / NCHW / ragged last tile) each thread stores its own row directly as before.
-    const bool geglu = p.act == TG_ACT_GEGLU;
-    const long long ocol0 = geglu ? (col0 >> 1) : col0;
-    const bool aligned = !row_ok || (((reinterpret_cast<uintptr_t>(p.out) + 2 * (obase + ocol0)) & 15) == 0);
-    const bool staged = p.ostage && !p.out_fp32 && p.ocol == 1 && (col0 + 16 * nch <= p.N) && __all_sync(0xffffffffu, aligned);
-    const uint32_t stg = staged ? ostg_row : 0u;
     if (row_ok) {
-      if (col0 < p.N) epilogue_chunk<T>(p, raw0, col0, obase, rbase, rbias, sb + c0, fast[i], rq[i][0], rq[i][1], stg, 0, lane);
+      if (col0 < p.N) epilogue_chunk<T>(p, raw0, col0, obase, rbase, rbias, sb + c0, fast[i], rq[i][0], rq[i][1]);
       if (nch == 2 && col0 + 16 < p.N)
-        epilogue_chunk<T>(p, raw1, col0 + 16, obase, rbase, rbias, sb + c0 + 16, fast[i], rq[i][2], rq[i][3], stg, 1, lane);
-    }
-    if (staged) {
-      // 16-byte chunks per row in this round: 4 (32 columns), 2 (16 columns, or 32 GEGLU columns), 1 (16 GEGLU columns)
-      const int ch16 = geglu ? nch : 2 * nch;
-      const int sh = (ch16 == 4) ? 2 : (ch16 == 2 ? 1 : 0);
-      __syncwarp();
-      for (int it = 0; it < ch16; ++it) {
-        const int rr = (it << (5 - sh)) + (lane >> sh), ch = lane & (ch16 - 1);
-        const long long ob = __shfl_sync(0xffffffffu, obase, rr);
-        const int ok = __shfl_sync(0xffffffffu, static_cast<int>(row_ok), rr);
-        const uint4 u = lds16(ostg_warp + rr * 64 + ((ch ^ (rr >> 1)) & 3) * 16);
-        if (ok) st16(reinterpret_cast<T*>(p.out) + ob + ocol0 + ch * 8, u);
-      }
-      __syncwarp();                              // the tile is rewritten by the next round
+        epilogue_chunk<T>(p, raw1, col0 + 16, obase, rbase, rbias, sb + c0 + 16, fast[i], rq[i][2], rq[i][3]);
     }
   }
 }
@@ -414,7 +562,7 @@ template <typename T>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
-               const __grid_constant__ TapGemmParams p) {
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ TapGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   if (TG_ALIGN_PAD < 1024 && base - smem_u32(smem_raw) > static_cast<uint32_t>(TG_ALIGN_PAD)) {
@@ -425,7 +573,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t BST = static_cast<uint32_t>(p.b_stage);
   const uint32_t sA = base;
   const uint32_t sB = base + NS * TG_A_STAGE;
-  const uint32_t bars = base + TG_STAGES * (TG_A_STAGE + TG_B_STAGE);
+  const uint32_t ostg = base + TG_STAGES * (TG_A_STAGE + TG_B_STAGE);   // epilogue store boxes (1024-byte aligned)
+  const uint32_t bars = ostg + TG_OSTG_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (TG_MAX_STAGES + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * TG_MAX_STAGES + a); };
@@ -447,6 +596,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA2)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB2)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
   }
   if (warp == TG_EPI_WARPS + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
@@ -530,13 +680,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       const int acc = iter & 1, aphase = (iter >> 1) & 1;
       const TileCoord c = decode_tile(p, tile);
-      epilogue_tile<T>(p, c, row, warp, j1, j2, j3, j4, acc, aphase, tmem_base, s_bias, tfull_bar(acc),
-                       iter == 0 && threadIdx.x == 0);
+      epilogue_tile<T>(p, &tmO, c, tile / p.n_tiles, row, warp, j1, j2, j3, j4, acc, aphase, tmem_base, s_bias, ostg,
+                       tfull_bar(acc), iter == 0 && threadIdx.x == 0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (iter == 0 && threadIdx.x == 0) tg_stamp(p, 9);                        // first tile stored
     }
+    if (p.tma_out && lane == 0) bulk_wait_all();      // the store boxes live in this CTA's shared memory
     if (threadIdx.x == 0) tg_stamp(p, 10);
   }
 

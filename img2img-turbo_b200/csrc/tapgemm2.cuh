@@ -27,7 +27,7 @@ constexpr int TG2_HALO_BYTES = TG2_HALO_H * TG2_HALO_W * TG_BK * 2;   // 36,864
 constexpr int TG2_HALO_STAGES = 2;
 constexpr int TG2_A2_STAGES = 2;
 #else
-constexpr int TG2_HALO_STAGES = (TG_EPI_WARPS == 16) ? 2 : 3;   // the 16-warp build needs the smem for its staging tiles
+constexpr int TG2_HALO_STAGES = 2;   // two 36 KB halo tiles (each serves nine taps) leave room for the 32 KB of epilogue store boxes
 constexpr int TG2_A2_STAGES = 0;
 #endif
 constexpr int TG2_HALO_REGION = TG2_HALO_STAGES * TG2_HALO_BYTES + TG2_A2_STAGES * TG_A_STAGE;   // [halo stages][A2 stages]
@@ -102,7 +102,8 @@ template <typename T>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
-                const __grid_constant__ CUtensorMap tmH, const __grid_constant__ TapGemmParams p) {
+                const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmO,
+                const __grid_constant__ TapGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   if (TG_ALIGN_PAD < 1024 && base - smem_u32(smem_raw) > static_cast<uint32_t>(TG_ALIGN_PAD)) {
@@ -114,7 +115,8 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t BST = static_cast<uint32_t>(p.b_stage);
   const uint32_t sA = base;
   const uint32_t sB = base + (p.halo ? TG2_HALO_REGION : NS * TG_A_STAGE);
-  const uint32_t bars = base + TG2_DATA_BYTES;
+  const uint32_t ostg = base + TG2_DATA_BYTES;                // epilogue store boxes (1024-byte aligned)
+  const uint32_t bars = ostg + TG_OSTG_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (TG_MAX_STAGES + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * TG_MAX_STAGES + a); };
@@ -165,6 +167,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA2)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB2)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmH)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
   }
   cluster_sync_all();                                   // peer barriers initialised before any remote arrive / TMEM alloc
   if (warp == TG_EPI_WARPS + 1) {
@@ -351,13 +354,14 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++iter) {
       const int acc = iter & 1, aphase = (iter >> 1) & 1;
       const TileCoord c = decode_pair(pt);
-      epilogue_tile<T>(p, c, row, warp, j1, j2, j3, j4, acc, aphase, tmem_base, s_bias, tfull_bar(acc),
-                       iter == 0 && threadIdx.x == 0);
+      epilogue_tile<T>(p, &tmO, c, 2 * (pt / p.n_tiles) + static_cast<int>(rank), row, warp, j1, j2, j3, j4, acc, aphase,
+                       tmem_base, s_bias, ostg, tfull_bar(acc), iter == 0 && threadIdx.x == 0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
       if (iter == 0 && threadIdx.x == 0) tg_stamp(p, 9);                        // first tile stored
     }
+    if (p.tma_out && lane == 0) bulk_wait_all();      // the store boxes live in this CTA's shared memory
     if (threadIdx.x == 0) tg_stamp(p, 10);
   }
 

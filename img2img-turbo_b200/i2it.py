@@ -28,7 +28,7 @@ _DT2TORCH = {F16: torch.float16, BF16: torch.bfloat16}
 SYMBOLS = [
     "i2it_default_config", "i2it_create", "i2it_destroy", "i2it_last_error", "i2it_set_weight",
     "i2it_set_adapter_scale", "i2it_finalize_weights", "i2it_workspace_bytes", "i2it_forward",
-    "i2it_set_text", "i2it_forward_u8", "i2it_prep_launch_count", "i2it_launch_count", "i2it_profile", "i2it_read_stage", "i2it_op_conv2d", "i2it_op_group_norm", "i2it_op_layer_norm",
+    "i2it_set_text", "i2it_encode_text", "i2it_forward_u8", "i2it_prep_launch_count", "i2it_launch_count", "i2it_profile", "i2it_read_stage", "i2it_op_conv2d", "i2it_op_group_norm", "i2it_op_layer_norm",
     "i2it_op_attention", "i2it_op_upsample2x",
 ]
 
@@ -39,6 +39,7 @@ class Config(C.Structure):
         ("unet_channels", C.c_int * 4), ("unet_heads", C.c_int * 4),
         ("cross_dim", C.c_int), ("temb_dim", C.c_int), ("vae_channels", C.c_int * 4),
         ("scaling_factor", C.c_float), ("keep_stages", C.c_int), ("use_cuda_graph", C.c_int),
+        ("text_heads", C.c_int), ("text_act", C.c_int),
     ]
 
 
@@ -69,6 +70,7 @@ def load_library(path: Optional[str] = None):
     lib.i2it_workspace_bytes.argtypes = [vp, ci, ci, ci, C.POINTER(C.c_size_t)]
     lib.i2it_forward.argtypes = [vp, vp, vp, ci, vp, vp, cf, vp, vp, ci, ci, ci, ci, vp]
     lib.i2it_set_text.argtypes = [vp, vp, ci, vp]
+    lib.i2it_encode_text.argtypes = [vp, vp, ci, vp, vp]
     lib.i2it_forward_u8.argtypes = [vp, vp, ci, vp, ci, vp, vp, cf, vp, vp, ci, ci, ci, ci, vp]
     lib.i2it_prep_launch_count.argtypes = [vp, C.POINTER(ci)]
     lib.i2it_launch_count.argtypes = [vp, ci, ci, ci, ci, C.POINTER(ci)]
@@ -99,7 +101,8 @@ class Engine:
     """One engine per (device, stream).  Thin, typed wrapper over the C handle."""
 
     def __init__(self, dtype: torch.dtype = torch.bfloat16, model_kind: int = PIX2PIX, cfg: Optional[dict] = None,
-                 device: Optional[int] = None, keep_stages: bool = False, use_cuda_graph: bool = True):
+                 device: Optional[int] = None, keep_stages: bool = False, use_cuda_graph: bool = True,
+                 text_heads: int = 0, text_act: str = "gelu"):
         if not torch.cuda.is_available():
             raise RuntimeError("libi2it needs a CUDA device (B200 / sm_100a); no CPU fallback exists")
         self.lib = load_library()
@@ -111,6 +114,8 @@ class Engine:
         c.device = torch.cuda.current_device() if device is None else device
         c.keep_stages = int(keep_stages)
         c.use_cuda_graph = int(use_cuda_graph)
+        c.text_heads = int(text_heads)                       # 0: hidden / 64
+        c.text_act = 1 if text_act == "quick_gelu" else 0
         if cfg is not None:
             for i in range(4):
                 c.unet_channels[i] = cfg["unet_channels"][i]
@@ -170,6 +175,14 @@ class Engine:
             raise ValueError(f"text_emb must be [1|B,77,{self.cross_dim}]")
         self._check(self.lib.i2it_set_text(self._h, _ptr(text_emb), text_emb.shape[0], _stream()), "i2it_set_text")
         self._text_batch = text_emb.shape[0]
+
+    def encode_text(self, tokens: torch.Tensor, hidden: int) -> torch.Tensor:
+        """CLIP text tower on the engine: tokens [B,77] (any integer dtype) -> last_hidden_state [B,77,hidden] in the engine dtype.
+        Needs the `text_encoder.*` tensors in the loaded state dict."""
+        ids = tokens.to(device="cuda", dtype=torch.int32).contiguous()
+        out = torch.empty(ids.shape[0], ids.shape[1], hidden, device="cuda", dtype=self.dtype)
+        self._check(self.lib.i2it_encode_text(self._h, _ptr(ids), ids.shape[0], _ptr(out), _stream()), "i2it_encode_text")
+        return out
 
     def _check_operands(self, B, H, W, text_emb, eps, others):
         for t in (text_emb, eps) + tuple(others):

@@ -52,6 +52,8 @@ typedef struct i2it_config {
   float scaling_factor;      /* 0.18215                                                                    */
   int keep_stages;           /* 1: keep named intermediate tensors readable via i2it_read_stage (tests)    */
   int use_cuda_graph;        /* 1: replay the forward as one CUDA graph when shapes and pointers repeat    */
+  int text_heads;            /* CLIP text tower: attention heads (16; head_dim must be 64); 0 = hidden/64  */
+  int text_act;              /* CLIP text tower MLP activation: 0 = gelu (SD-Turbo), 1 = quick_gelu        */
 } i2it_config;
 
 /* Fill `cfg` with the SD-Turbo configuration. */
@@ -112,6 +114,12 @@ int i2it_forward(i2it_handle* h, const void* x, const void* text_emb, int text_b
  * the stream reaches this point).  Must be called again after i2it_finalize_weights (the projections carry the LoRA scale).
  * Replaces the per-forward `attn2.to_k / attn2.to_v` calls under unet(...) at /root/reference/src/pix2pix_turbo.py:199. */
 int i2it_set_text(i2it_handle* h, const void* text_emb, int text_batch, void* stream);
+
+/* The CLIP text tower on the engine: tokens [batch, 77] int32 (device) -> last_hidden_state
+ * [batch, 77, hidden] (device, handle dtype), i.e. `self.text_encoder(tokens)[0]` of /root/reference/src/pix2pix_turbo.py:190-196
+ * and cyclegan_turbo.py:251-253.  Needs the "text_encoder.<transformers CLIPTextModel key>" tensors registered with
+ * i2it_set_weight.  Enqueued on `stream` (no CUDA graph: a prompt is encoded once and cached by the caller). */
+int i2it_encode_text(i2it_handle* h, const int32_t* tokens, int batch, void* out, void* stream);
 
 /* i2it_forward with a uint8 HWC boundary: x_u8_hwc [batch, H, W, 3] and out_u8_hwc [batch, H, W, 3] are device pointers.
  * Input transform `in_mode` (I2IT_IN_*) and the output `ToPILImage()(out*0.5+0.5)` (src/inference_paired.py:72,

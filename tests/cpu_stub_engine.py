@@ -22,7 +22,7 @@ CALLS = []          # (method, summary) log the tests inspect
 
 
 class StubEngine:
-    def __init__(self, dtype=torch.bfloat16, model_kind=0, cfg=None, device=None, keep_stages=False, use_cuda_graph=True):
+    def __init__(self, dtype=torch.bfloat16, model_kind=0, cfg=None, device=None, keep_stages=False, use_cuda_graph=True, **kw):
         import weights as W
         self.dtype, self.kind, self.cfg = dtype, model_kind, cfg or W.SD_TURBO
         self.cross_dim = self.cfg["cross_dim"]
@@ -30,7 +30,7 @@ class StubEngine:
         CALLS.append(("create", str(dtype)))
 
     def load_state_dict(self, sd):
-        self.sd = {k: v.detach().float().cpu() for k, v in sd.items()}
+        self.sd.update({k: v.detach().float().cpu() for k, v in sd.items() if not k.startswith("text_encoder.")})
 
     def set_adapter_scale(self, name, s):
         self.scales[name] = s
