@@ -662,6 +662,11 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o_in) {
     o2.x2 = o_in.res; o2.w2 = &ident; o2.res = nullptr; o2.x2_identity = true;
     return conv(P, x, w, o2);
   }
+  if (o_in.stride == 2 && ((x.H | x.W) & 1)) {
+    // odd-sized map (latent of an image that is a multiple of 8 but not of 64): the right / bottom zero padding is materialised
+    // once so that the 5-D parity view stays a plain box; Ho = ceil(H/2) as F.conv2d(stride=2, padding=1) gives
+    return conv(P, pad_even(P, x), w, o_in);
+  }
   const ConvOpts& o = o_in;
   const bool sub = o.subpixel_phase >= 0;
   const int k = o.ksize, taps = sub ? 4 : k * k;
@@ -972,17 +977,33 @@ Act Engine::layer_norm(Plan& P, const Act& x, const NormW& nw, bool to_io_out) {
   return y;
 }
 
-Act Engine::upsample2x(Plan& P, const Act& x) {
-  Act y = alloc_act(P, x.N, 2 * x.H, 2 * x.W, x.C);
-  const long long total = static_cast<long long>(x.N) * 4 * x.H * x.W * (x.C / 8);
+Act Engine::upsample_to(Plan& P, const Act& x, int Ho, int Wo) {
+  Act y = alloc_act(P, x.N, Ho, Wo, x.C);
+  const long long total = static_cast<long long>(x.N) * Ho * Wo * (x.C / 8);
   const uint16_t* xp = x.p;
   uint16_t* yp = y.p;
   const int ldx = x.ld, ldy = y.ld, H = x.H, W = x.W, C = x.C, dt = dtype;
+  const float sh = static_cast<float>(H) / static_cast<float>(Ho), sw = static_cast<float>(W) / static_cast<float>(Wo);
   const double N_ = x.N;
   add_op(P, [=](cudaStream_t st) {
-    DISPATCH_T(dt, (launch_k(upsample2x_kernel<T>, dim3(ceil_div(total, 256)), dim3(256), 0, st, 0, reinterpret_cast<const T*>(xp), ldx,
-                                                                             reinterpret_cast<T*>(yp), ldy, H, W, C, total)));
-  }, "upsample2x", 0, 2.0 * 5.0 * N_ * H * W * C);
+    DISPATCH_T(dt, (launch_k(upsample_nearest_kernel<T>, dim3(ceil_div(total, 256)), dim3(256), 0, st, 0, reinterpret_cast<const T*>(xp),
+                             ldx, reinterpret_cast<T*>(yp), ldy, H, W, Ho, Wo, sh, sw, C, total)));
+  }, "upsample_nearest", 0, 2.0 * N_ * C * (1.0 * H * W + 1.0 * Ho * Wo));
+  return y;
+}
+
+Act Engine::pad_even(Plan& P, const Act& x) {
+  const int H2 = x.H + (x.H & 1), W2 = x.W + (x.W & 1);
+  if (H2 == x.H && W2 == x.W && x.ld == x.C) return x;
+  Act y = alloc_act(P, x.N, H2, W2, x.C);
+  const long long total = static_cast<long long>(x.N) * H2 * W2 * (x.C / 8);
+  const uint16_t* xp = x.p;
+  uint16_t* yp = y.p;
+  const int ldx = x.ld, H = x.H, W = x.W, C = x.C, dt = dtype;
+  add_op(P, [=](cudaStream_t st) {
+    DISPATCH_T(dt, (launch_k(pad_copy_kernel<T>, dim3(ceil_div(total, 256)), dim3(256), 0, st, 0, reinterpret_cast<const T*>(xp), ldx,
+                             reinterpret_cast<T*>(yp), H, W, H2, W2, C, total)));
+  }, "pad_even", 0, 4.0 * total * 8);
   return y;
 }
 
@@ -1044,7 +1065,7 @@ Act Engine::attention(Plan& P, const Act& q, const Act& k, const Act& vt, int B,
                       int kv_batch) {
   if (d == FA_D && use_flash) return flash_attention(P, q, k, vt, B, Nq, Nk, heads, kv_batch);
   I2IT_CHECK(d % 64 == 0 && (d <= 256 || d % 256 == 0), "attention: head dim must be a multiple of 64");
-  I2IT_CHECK(Nk <= 4096, "attention: Nk > 4096 needs the fused kernel");
+
   I2IT_CHECK(kv_batch == B || kv_batch == 1, "attention: kv batch must be 1 or B");
   const int C = heads * d, lds = round_up(Nk, 8);
   const long long rows = static_cast<long long>(B) * heads * Nq;
@@ -1092,7 +1113,12 @@ Act Engine::attention(Plan& P, const Act& q, const Act& k, const Act& vt, int B,
   }
   {  // P = softmax(S)
     const int dt = dtype;
-    if (Nk > 1024) {
+    if (Nk > 4096) {
+      add_op(P, [=](cudaStream_t st) {
+        DISPATCH_T(dt, (launch_k(softmax_long_kernel<T>, dim3(static_cast<unsigned>(rows)), dim3(256), 0, st, 0, S, lds, reinterpret_cast<T*>(Pm),
+                                                                                          lds, Nk, lds)));
+      }, "softmax", 0, 6.0 * rows * Nk);
+    } else if (Nk > 1024) {
       add_op(P, [=](cudaStream_t st) {
         DISPATCH_T(dt, (launch_k(softmax_kernel<T, 128>, dim3(static_cast<unsigned>(rows)), dim3(128), 0, st, 0, S, lds, reinterpret_cast<T*>(Pm), lds,
                                                                                           rows, Nk, lds)));
@@ -1272,7 +1298,7 @@ void Engine::encode_text(const int* tokens, int batch, void* out, cudaStream_t s
 }
 
 void Engine::forward(const IO& io_in, int B, int H, int W, int direction, int text_batch, cudaStream_t st) {
-  I2IT_CHECK(H % 64 == 0 && W % 64 == 0 && H > 0 && W > 0, "H and W must be positive multiples of 64");
+  I2IT_CHECK(H % 8 == 0 && W % 8 == 0 && H > 0 && W > 0, "H and W must be positive multiples of 8 (as the reference CLIs crop them)");
   I2IT_CHECK(B > 0 && (text_batch == 1 || text_batch == B), "text_batch must be 1 or batch");
   IO io = io_in;
   const int io_mode = (io.x_u8 ? IO_U8_IN : 0) | (io.out_u8 ? IO_U8_OUT : 0);

@@ -189,7 +189,9 @@ class Engine {
   Act linear(Plan& P, const Act& x, const PW& w, const Act* res = nullptr, int act = TG_ACT_NONE, bool gn_out = false);
   Act group_norm(Plan& P, const Act& x, const NormW& nw, float eps, bool silu);
   Act layer_norm(Plan& P, const Act& x, const NormW& nw, bool to_io_out = false);
-  Act upsample2x(Plan& P, const Act& x);
+  Act upsample2x(Plan& P, const Act& x) { return upsample_to(P, x, 2 * x.H, 2 * x.W); }
+  Act upsample_to(Plan& P, const Act& x, int Ho, int Wo);          // F.interpolate(size=(Ho,Wo), mode="nearest")
+  Act pad_even(Plan& P, const Act& x);                               // zero-padded copy with even H and W
   void copy_channels(Plan& P, const Act& src, const Act& dst_slice);
   // V^T[b] = Wv X[b]^T (+ row bias): returns [B][C][ldv] as an Act with N=B,H=1,W=C,ld=ldv (C field = Ntok)
   Act vt_proj(Plan& P, const Act& x_tokens, int B, int ntok, const PW& wv);

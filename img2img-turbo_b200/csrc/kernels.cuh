@@ -285,6 +285,37 @@ __global__ void softmax_kernel(const float* __restrict__ s, long long lds, T* __
   }
 }
 
+// Row softmax for rows longer than 4096 logits (VAE attention of images larger than 512x512): one CTA of 256 threads per row,
+// three strided passes over the fp32 logits (max, sum, write) — the logits of one row (<= a few tens of KB) stay in L1/L2.
+template <typename T>
+__global__ void softmax_long_kernel(const float* __restrict__ s, long long lds, T* __restrict__ pr, long long ldp, int nk, int nk_pad) {
+  pdl_sync();
+  __shared__ float red[8];
+  const long long row = blockIdx.x;
+  const float* sr = s + row * lds;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < nk; c += 256) m = fmaxf(m, sr[c]);
+  m = warp_max(m);
+  if (lane == 0) red[w] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < nk; c += 256) sum += __expf(sr[c] - m);
+  sum = warp_sum(sum);
+  if (lane == 0) red[w] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[i];          // fixed order: reproducible
+  const float inv = 1.0f / sum;
+  T* o = pr + row * ldp;
+  for (int c = threadIdx.x; c < nk_pad; c += 256) o[c] = Elem<T>::from_f(c < nk ? __expf(sr[c] - m) * inv : 0.f);
+}
+
 // =============================================================================================
 // CLIP text embeddings: out[b, t, :] = token_embedding[ids[b, t]] + position_embedding[t]   (fp32 add, one rounding)
 // (transformers models/clip/modeling_clip.py CLIPTextEmbeddings.forward; reference call /root/reference/src/pix2pix_turbo.py:190-196)
@@ -477,21 +508,43 @@ __global__ void ddpm_step_kernel(const T* __restrict__ zin /*NHWC8*/, const T* _
   st16(dec_in + i * 8, make_uint4(Elem<T>::pack(o[0], o[1]), Elem<T>::pack(o[2], o[3]), 0u, 0u));
 }
 
-// nearest 2x upsample, NHWC, 16-byte vectors
+// nearest upsample to (Ho, Wo), NHWC, 16-byte vectors.  Index rule of F.interpolate(mode="nearest"): src = min(floor(dst * in/out),
+// in - 1) with the ratio in fp32 (exactly 2x when Ho = 2H).  diffusers Upsample2D passes an explicit output size when the latent
+// is not a multiple of 8 (UNet2DConditionModel.forward: forward_upsample_size), e.g. 14 -> 27 for a 560x840 image.
 template <typename T>
-__global__ void upsample2x_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int H, int W, int C,
-                                  long long total /* B*2H*2W*(C/8) */) {
+__global__ void upsample_nearest_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int H, int W, int Ho, int Wo,
+                                        float sh, float sw, int C, long long total /* B*Ho*Wo*(C/8) */) {
   pdl_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int vecs = C >> 3;
   const int v = static_cast<int>(i % vecs);
   long long p = i / vecs;
-  const int ox = static_cast<int>(p % (2 * W)); p /= (2 * W);
-  const int oy = static_cast<int>(p % (2 * H));
-  const long long n = p / (2 * H);
-  const uint4 u = ld_nc16(x + ((n * H + (oy >> 1)) * W + (ox >> 1)) * ldx + v * 8);
-  st16(y + ((n * 2 * H + oy) * 2 * W + ox) * ldy + v * 8, u);
+  const int ox = static_cast<int>(p % Wo); p /= Wo;
+  const int oy = static_cast<int>(p % Ho);
+  const long long n = p / Ho;
+  const int sy = min(static_cast<int>(floorf(oy * sh)), H - 1), sx = min(static_cast<int>(floorf(ox * sw)), W - 1);
+  const uint4 u = ld_nc16(x + ((n * H + sy) * W + sx) * ldx + v * 8);
+  st16(y + ((n * Ho + oy) * Wo + ox) * ldy + v * 8, u);
+}
+
+// zero-padded copy [B,H,W,C] -> [B,H2,W2,C] (H2 >= H, W2 >= W): a stride-2 conv over an odd-sized map reads the 5-D parity view
+// of an EVEN-sized tensor, and its right/bottom zero padding becomes real zeros
+template <typename T>
+__global__ void pad_copy_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int H, int W, int H2, int W2, int C,
+                                long long total /* B*H2*W2*(C/8) */) {
+  pdl_sync();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int vecs = C >> 3;
+  const int v = static_cast<int>(i % vecs);
+  long long p = i / vecs;
+  const int ox = static_cast<int>(p % W2); p /= W2;
+  const int oy = static_cast<int>(p % H2);
+  const long long n = p / H2;
+  uint4 u = make_uint4(0u, 0u, 0u, 0u);
+  if (oy < H && ox < W) u = ld_nc16(x + ((n * H + oy) * W + ox) * ldx + v * 8);
+  st16(y + ((n * H2 + oy) * W2 + ox) * C + v * 8, u);
 }
 
 // strided 2-D copy of 16-byte vectors: rows x (C/8) vectors (torch.cat along channels)

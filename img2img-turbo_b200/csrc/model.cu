@@ -312,7 +312,10 @@ Act Engine::build_unet(Plan& P, const Act& z, int text_batch, bool text_cached) 
       if (i > 0) s = unet_xformer(P, blk + ".attentions." + std::to_string(j), s, hcount, text_batch, last);
     }
     if (i < 3) {
-      s = upsample2x(P, s);
+      // Upsample2D: 2x nearest, or — when the latent is not a multiple of 8 (UNet2DConditionModel.forward: forward_upsample_size)
+      // — nearest to the spatial size of the next skip connection (e.g. 14 -> 27 columns for a 560x840 image)
+      const Act& nxt = res.back();
+      s = upsample_to(P, s, nxt.H, nxt.W);
       s = conv(P, s, prep(blk + ".upsamplers.0.conv", {blk + ".upsamplers.0.conv"}), ConvOpts());
     }
   }

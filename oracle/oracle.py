@@ -306,6 +306,10 @@ def unet_forward(sd: SD, prefix: str, z: torch.Tensor, text: torch.Tensor, cfg=S
     s = _transformer(sd, f"{u}.mid_block.attentions.0", s, text, heads[-1], cfg, scales)
     s = _unet_resnet(sd, f"{u}.mid_block.resnets.1", s, emb_act, cfg, scales)
     rheads = heads[::-1]
+    # diffusers UNet2DConditionModel.forward: if any latent dim is not a multiple of 2**num_upsamplers, every non-final up block
+    # is told the spatial size of the next skip connection (`upsample_size = down_block_res_samples[-1].shape[2:]`) and
+    # Upsample2D interpolates to that size instead of by a factor 2 (models/resnet.py Upsample2D.forward: output_size)
+    forward_upsample_size = any(d % (2 ** (nb - 1)) != 0 for d in z.shape[-2:])
     for i in range(nb):
         for j in range(L + 1):
             s = torch.cat([s, res.pop()], dim=1)
@@ -313,7 +317,10 @@ def unet_forward(sd: SD, prefix: str, z: torch.Tensor, text: torch.Tensor, cfg=S
             if i > 0:
                 s = _transformer(sd, f"{u}.up_blocks.{i}.attentions.{j}", s, text, rheads[i], cfg, scales)
         if i < nb - 1:
-            s = F.interpolate(s, scale_factor=2.0, mode="nearest")
+            if forward_upsample_size:
+                s = F.interpolate(s, size=tuple(res[-1].shape[2:]), mode="nearest")
+            else:
+                s = F.interpolate(s, scale_factor=2.0, mode="nearest")
             s = conv2d(sd, f"{u}.up_blocks.{i}.upsamplers.0.conv", s, scales, padding=1)
     assert not res
     s = F.silu(group_norm(sd, f"{u}.conv_norm_out", s, cfg["unet_groups"], 1e-5))

@@ -71,8 +71,9 @@ def _stages(e, pick):
 
 # bounds: relative mean error per stage vs the fp32 oracle (16-bit storage of every activation; the DDPM step multiplies the
 # UNet error by 14.6 and /0.18215 by another 5.5 before the decoder — SURVEY fact 6)
-BOUNDS_FP16 = {"skip0": 5e-3, "skip3": 1e-2, "latent": 2e-2, "model_pred": 3e-2, "x_denoised": 6e-2, "pre_clamp": 1.5e-1}
-BOUNDS_BF16 = {"skip0": 2e-2, "skip3": 4e-2, "latent": 8e-2, "model_pred": 1.2e-1, "x_denoised": 2.5e-1, "pre_clamp": 5e-1}
+# measured on B200 (profiles/r02b_parity_bands.json): fp16 0.02 / 0.14 / 0.06-0.09 / 0.2 / 0.2 / 0.15-0.28 %, bf16 x 6-8; bounds = ~3x that
+BOUNDS_FP16 = {"skip0": 1e-3, "skip3": 5e-3, "latent": 3e-3, "model_pred": 7e-3, "x_denoised": 7e-3, "pre_clamp": 1e-2}
+BOUNDS_BF16 = {"skip0": 8e-3, "skip3": 4e-2, "latent": 2e-2, "model_pred": 5e-2, "x_denoised": 5e-2, "pre_clamp": 7e-2}
 
 
 @pytest.fixture(scope="module")
@@ -114,8 +115,8 @@ def test_config3_cyclegan_fp16_batch16(cyclegan_fp16, direction):
         for name, r in refs.items():
             stage_report(f"{tag}_img{pick}", name, mine[name], r, BOUNDS_FP16[name])
         stage_report(f"{tag}_img{pick}", "x_denoised", lat[pick:pick + 1], st["x_denoised"], BOUNDS_FP16["x_denoised"])
-        row = stage_report(f"{tag}_img{pick}", "image", out[pick:pick + 1], ref, 1e-1)
-        assert row["mean_abs_err"] < 0.02, row
+        row = stage_report(f"{tag}_img{pick}", "image", out[pick:pick + 1], ref, 1e-2)
+        assert row["mean_abs_err"] < 3e-3, row
     _flush_bands()
 
 
@@ -152,8 +153,8 @@ def test_config4_pix2pix_stochastic_bf16(capsys):
     for name, rr in refs.items():
         stage_report(tag, name, mine[name], rr, BOUNDS_BF16[name])
     stage_report(tag, "x_denoised", lat[pick:pick + 1], st["x_denoised"], BOUNDS_BF16["x_denoised"])
-    row = stage_report(tag, "image", out[pick:pick + 1], ref, 3e-1)
-    assert row["mean_abs_err"] < 0.05, row
+    row = stage_report(tag, "image", out[pick:pick + 1], ref, 5e-2)
+    assert row["mean_abs_err"] < 1.2e-2, row
     # gamma matters: the deterministic fold of the same weights gives a different image
     e.finalize(1.0, 1.0, 1.0, 1.0)
     out_r1 = e.forward(x.to(dt).cuda(), text.to(dt).cuda(), eps.to(dt).cuda(), noise.to(dt).cuda(), 1.0)
@@ -187,6 +188,6 @@ def test_config2_stage_table_bf16_and_fp16():
         for name, rr in refs.items():
             stage_report(tag, name, mine[name], rr, bounds[name])
         stage_report(tag, "x_denoised", lat, st["x_denoised"], bounds["x_denoised"])
-        stage_report(tag, "image", out, ref, 3e-1)
+        stage_report(tag, "image", out, ref, 7e-2 if dt == torch.bfloat16 else 1e-2)
         e.close()
     _flush_bands()

@@ -185,6 +185,34 @@ def test_non_square_resolution():
     assert m <= 1.5 * m_ref + 2e-3 and mx <= 1.5 * x_ref + 5e-2, (m, m_ref, mx, x_ref)
 
 
+@pytest.mark.parametrize("hw", [(72, 104), (136, 200)])
+def test_resolutions_that_are_multiples_of_8_not_64(hw):
+    """The reference CLIs crop to multiples of 8 (inference_paired.py:38-41; the shipped bird example is 560x840): latent sizes
+    like 9x13 / 17x25 make the UNet's stride-2 convs round up and its up path interpolate to the skip's size
+    (forward_upsample_size); the VAE sees ragged tiles at every level."""
+    import oracle as O
+    import weights as W
+    cfg, dt = W.TINY, torch.bfloat16
+    H, Wd = hw
+    sd = W.make_state_dict("pix2pix", cfg, seed=0, perturb_norm=True)
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(2, 1, H, Wd, generator=g) < 0.1).float().expand(-1, 3, -1, -1).contiguous()
+    text = torch.randn(1, 77, cfg["cross_dim"], generator=g)
+    eps = torch.randn(2, 4, H // 8, Wd // 8, generator=g)
+    q = lambda t: t.to(dt).float()
+    with torch.no_grad():
+        ref = O.pix2pix_forward(sd, q(x), q(text), q(eps), cfg)
+        ref16 = O.pix2pix_forward({k: v.to(dt) for k, v in sd.items()}, x.to(dt), text.to(dt), eps.to(dt), cfg)
+    e = _engine("pix2pix", cfg, dt, sd)
+    e.finalize(1.0, 1.0, 1.0, -1.0)
+    out = e.forward(x.to(dt).cuda(), text.to(dt).cuda(), eps.to(dt).cuda())
+    torch.cuda.synchronize()
+    m_ref, x_ref = _err(ref16, ref)
+    m, mx = _err(out, ref)
+    assert out.shape == (2, 3, H, Wd) and torch.isfinite(out.float()).all()
+    assert m <= 1.5 * m_ref + 2e-3 and mx <= 1.5 * x_ref + 5e-2, (m, m_ref, mx, x_ref)
+
+
 @pytest.fixture(scope="module")
 def full_model():
     import weights as W

@@ -139,3 +139,28 @@ def test_batch_independence(tiny_sd):
         full = O.pix2pix_forward(tiny_sd, x, text, eps, cfg)
         one = O.pix2pix_forward(tiny_sd, x[1:], text[1:], eps[1:], cfg)
     assert (full[1:] - one).abs().max() < 1e-4
+
+
+def test_unet_sizes_that_are_not_multiples_of_eight():
+    """Images that are multiples of 8 but not of 64 (the CLIs only crop to %8: a 560x840 example ships with the reference) give
+    latents like 70x105: stride-2 convs round up (35x53, 18x27, 9x14) and the up path interpolates to the skip's size
+    (diffusers forward_upsample_size).  Shape bookkeeping + the two interpolation rules agree where both apply."""
+    cfg = W.TINY
+    sd = W.make_state_dict("pix2pix", cfg, seed=0, perturb_norm=True)
+    g = torch.Generator().manual_seed(0)
+    for h, w in ((9, 13), (10, 7)):
+        z = torch.randn(1, 4, h, w, generator=g)
+        text = torch.randn(1, 77, cfg["cross_dim"], generator=g)
+        with torch.no_grad():
+            out = O.unet_forward(sd, "unet.", z, text, cfg, {"default": 1.0})
+        assert out.shape == (1, 4, h, w) and torch.isfinite(out).all()
+    # on a multiple-of-8 latent, interpolate(size=2H) == interpolate(scale_factor=2): the explicit-size rule is a superset
+    x = torch.randn(1, 3, 6, 5, generator=g)
+    assert torch.equal(torch.nn.functional.interpolate(x, size=(12, 10), mode="nearest"),
+                       torch.nn.functional.interpolate(x, scale_factor=2.0, mode="nearest"))
+    # whole path at 72x104 (latent 9x13)
+    xin = (torch.rand(1, 1, 72, 104, generator=g) < 0.1).float().expand(-1, 3, -1, -1).contiguous()
+    eps = torch.randn(1, 4, 9, 13, generator=g)
+    with torch.no_grad():
+        img = O.pix2pix_forward(sd, xin, torch.randn(1, 77, cfg["cross_dim"], generator=g), eps, cfg)
+    assert img.shape == (1, 3, 72, 104) and torch.isfinite(img).all()
