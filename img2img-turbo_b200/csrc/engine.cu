@@ -922,7 +922,7 @@ Act Engine::group_norm(Plan& P, const Act& x, const NormW& nw, float eps, bool s
   const int chunks = std::max(1, std::min(env_chunks, ceil_div(HW, rows * 4)));
   const int pix = ceil_div(HW, chunks);
   I2IT_CHECK(chunks <= 1024, "group_norm: too many chunks");
-  auto partial = alloc_raw(P, static_cast<size_t>(x.N) * chunks * 64 * sizeof(float));
+  auto partial = alloc_raw(P, std::max(static_cast<size_t>(x.N) * chunks * 64 * sizeof(float), static_cast<size_t>(x.N) * 4 * 32 * sizeof(double)* 2));
   auto stats = alloc_raw(P, static_cast<size_t>(x.N) * 64 * sizeof(float));
   Act y = alloc_act(P, x.N, x.H, x.W, C);
   float* d_part = static_cast<float*>(partial.get());
@@ -934,14 +934,22 @@ Act Engine::group_norm(Plan& P, const Act& x, const NormW& nw, float eps, bool s
   const float* g = nw.g;
   const float* b = nw.b;
   const double inv_count = 1.0 / (static_cast<double>(HW) * cg);
+  const double2* d_part2 = nullptr;
+  int nchunk = 0;
   if (x.gn && use_gnepi && x.gn->C == C && x.gn->images == N) {
     // the producer's epilogue already summed the tensor: reduce its per-slot partials (no pass over the tensor itself)
     const GnPart gp = *x.gn;
     const float* pb = gp.buf;
     const int per_row = C / gp.red, epg = cg / gp.red;
+    I2IT_CHECK(per_row <= 640, "group_norm: too many partial entries per slot");
+    nchunk = std::max(1, std::min(4, gp.slots_per_image / 64));
+    const int e_lanes = std::min(256, pow2ceil(per_row));
+    double2* p2 = reinterpret_cast<double2*>(d_part);          // [N][nchunk][32] double2 fits the (N * chunks * 64 floats) block
+    d_part2 = p2;
+    const int nch = nchunk;
     add_op(P, [=](cudaStream_t st) {
-      launch_k(gn_finalize_part_kernel, dim3(32, N), dim3(256), 0, st, 0, pb, gp.phases, gp.images, gp.slots_per_image, per_row, epg,
-               inv_count, eps, d_stats);
+      launch_k(gn_part_reduce_kernel, dim3(nch, N), dim3(256), 0, st, 0, pb, gp.phases, gp.images, gp.slots_per_image, per_row, epg,
+               e_lanes, p2);
     }, "gn_final_part", 0, 8.0 * gp.phases * N * gp.slots_per_image * per_row);
   } else {
     add_op(P, [=](cudaStream_t st) {
@@ -953,7 +961,7 @@ Act Engine::group_norm(Plan& P, const Act& x, const NormW& nw, float eps, bool s
   add_op(P, [=](cudaStream_t st) {
     DISPATCH_T(dt, (launch_k(gn_apply_kernel<T>, dim3(chunks, N), dim3(threads), 0, st, 0,
                        reinterpret_cast<const T*>(xp), ximg, ldx, reinterpret_cast<T*>(yp), yimg, ldy, C, HW, cg, pix,
-                       d_stats, g, b, isilu)));
+                       d_stats, g, b, isilu, d_part2, nchunk, inv_count, eps)));
   }, "gn_apply", 0, 4.0 * N * HW * C);
   return y;     // (y carries no statistics: it is a different tensor)
 }

@@ -96,53 +96,89 @@ static __global__ void gn_finalize_kernel(const float* __restrict__ partial, int
   }
 }
 
-// Finalize from the partials a producing GEMM's epilogue wrote (TapGemmParams::gn_part): block (g, n) reduces group g of image n
-// over [phases][slots][entries-per-group] in a fixed order (double accumulation, reproducible, no atomics).
-static __global__ void gn_finalize_part_kernel(const float* __restrict__ part, int phases, int images, int slots, int per_row,
-                                               int epg, double inv_count, float eps, float* __restrict__ stats) {
+// First reduction level over the partials a producing GEMM's epilogue wrote (TapGemmParams::gn_part,
+// [phases][images][slots][per_row] x (sum, sumsq)): block (chunk, n) sums its share of image n's slots with COALESCED loads
+// (threads run along the per_row entries of a slot row), then folds the `epg` entries of each group -> out[n][chunk][32] in
+// double.  The last level (<= 4 chunks) is folded into gn_apply's prologue.  Fixed summation order: reproducible, no atomics.
+static __global__ void gn_part_reduce_kernel(const float* __restrict__ part, int phases, int images, int slots, int per_row,
+                                             int epg, int e_lanes /* pow2, <= 256 */, double2* __restrict__ out) {
   pdl_sync();
   __shared__ double2 red[256];
-  const int g = blockIdx.x, n = blockIdx.y;
-  double a = 0.0, b = 0.0;
-  const long long items = static_cast<long long>(slots) * epg;
-  for (int ph = 0; ph < phases; ++ph) {
-    const float2* base = reinterpret_cast<const float2*>(part) + (static_cast<long long>(ph) * images + n) * slots * per_row + g * epg;
-    for (long long i = threadIdx.x; i < items; i += 256) {
-      const long long sl = i / epg;
-      const int e = static_cast<int>(i - sl * epg);
-      const float2 v = base[sl * per_row + e];
-      a += static_cast<double>(v.x); b += static_cast<double>(v.y);
+  __shared__ double2 ent[640];                      // per_row <= 1280 / 2
+  const int n = blockIdx.y, c = blockIdx.x, nch = gridDim.x, t = threadIdx.x;
+  const int s0 = static_cast<int>(static_cast<long long>(c) * slots / nch), s1 = static_cast<int>(static_cast<long long>(c + 1) * slots / nch);
+  const int nsl = 256 / e_lanes, te = t % e_lanes, tsl = t / e_lanes;
+  for (int e0 = 0; e0 < per_row; e0 += e_lanes) {
+    const int e = e0 + te;
+    double a = 0.0, b = 0.0;
+    if (e < per_row) {
+      for (int ph = 0; ph < phases; ++ph) {
+        const float2* base = reinterpret_cast<const float2*>(part) + (static_cast<long long>(ph) * images + n) * slots * per_row + e;
+        int sl = s0 + tsl;
+        for (; sl + 3 * nsl < s1; sl += 4 * nsl) {           // 4 independent loads in flight
+          const float2 v0 = base[static_cast<long long>(sl) * per_row], v1 = base[static_cast<long long>(sl + nsl) * per_row];
+          const float2 v2 = base[static_cast<long long>(sl + 2 * nsl) * per_row], v3 = base[static_cast<long long>(sl + 3 * nsl) * per_row];
+          a += static_cast<double>(v0.x); b += static_cast<double>(v0.y);
+          a += static_cast<double>(v1.x); b += static_cast<double>(v1.y);
+          a += static_cast<double>(v2.x); b += static_cast<double>(v2.y);
+          a += static_cast<double>(v3.x); b += static_cast<double>(v3.y);
+        }
+        for (; sl < s1; sl += nsl) {
+          const float2 v = base[static_cast<long long>(sl) * per_row];
+          a += static_cast<double>(v.x); b += static_cast<double>(v.y);
+        }
+      }
     }
-  }
-  red[threadIdx.x] = make_double2(a, b);
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) { red[threadIdx.x].x += red[threadIdx.x + o].x; red[threadIdx.x].y += red[threadIdx.x + o].y; }
+    red[t] = make_double2(a, b);
+    __syncthreads();
+    if (tsl == 0 && e < per_row) {
+      double2 acc = red[te];
+      for (int k = 1; k < nsl; ++k) { acc.x += red[k * e_lanes + te].x; acc.y += red[k * e_lanes + te].y; }
+      ent[e] = acc;
+    }
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    const double mean = red[0].x * inv_count;
-    double var = red[0].y * inv_count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    stats[(n * 32 + g) * 2] = static_cast<float>(mean);
-    stats[(n * 32 + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  if (t < 32) {
+    double2 acc = make_double2(0.0, 0.0);
+    for (int k = 0; k < epg; ++k) { acc.x += ent[t * epg + k].x; acc.y += ent[t * epg + k].y; }
+    out[(static_cast<long long>(n) * nch + c) * 32 + t] = acc;
   }
 }
 
 template <typename T>
 __global__ void gn_apply_kernel(const T* __restrict__ x, long long ximg, int ldx, T* __restrict__ y, long long yimg,
                                 int ldy, int C, int HW, int cg, int pix_per_cta, const float* __restrict__ stats,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu) {
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+                                const double2* __restrict__ part2 = nullptr, int nchunk = 0, double inv_count = 0.0,
+                                float eps = 0.f) {
   pdl_sync();
   const int vecs = C >> 3;
   const int vx = threadIdx.x % vecs, vy = threadIdx.x / vecs, rows = blockDim.x / vecs;
   const int n = blockIdx.y;
   if (vy >= rows) return;
   float sc[8], sh[8];
+  int gprev = -1;
+  float mean = 0.f, rstd = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = vx * 8 + i, g = c / cg;
-    const float mean = stats[(n * 32 + g) * 2], rstd = stats[(n * 32 + g) * 2 + 1];
+    if (g != gprev) {
+      gprev = g;
+      if (part2) {             // statistics came from the producing GEMM's epilogue: fold the last (<= 4) chunk partials here
+        double a = 0.0, b = 0.0;
+        for (int k = 0; k < nchunk; ++k) {
+          const double2 v = part2[(static_cast<long long>(n) * nchunk + k) * 32 + g];
+          a += v.x; b += v.y;
+        }
+        const double m = a * inv_count;
+        double var = b * inv_count - m * m;
+        if (var < 0.0) var = 0.0;
+        mean = static_cast<float>(m);
+        rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      } else {
+        mean = stats[(n * 32 + g) * 2]; rstd = stats[(n * 32 + g) * 2 + 1];
+      }
+    }
     sc[i] = rstd * gamma[c];
     sh[i] = beta[c] - mean * sc[i];
   }

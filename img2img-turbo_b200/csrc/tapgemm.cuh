@@ -25,7 +25,10 @@ namespace i2it {
 constexpr int TG_BM = 128;             // rows per tile (= TMEM lanes)
 constexpr int TG_BK = 64;              // K elements per stage (= 128 B = one swizzle atom)
 constexpr int TG_STAGES = 4;            // stages when the B tile is the full 32 KiB; smaller tiles get more (<= TG_MAX_STAGES)
-constexpr int TG_MAX_STAGES = 8;
+#ifndef I2IT_MAX_STAGES
+#define I2IT_MAX_STAGES 16          // `make STAGES8=1` builds the round-1 ring depth (8) into its own library for A/B runs
+#endif
+constexpr int TG_MAX_STAGES = I2IT_MAX_STAGES;   // small B tiles (BN <= 128) need more stages for the same lookahead in TIME
 constexpr int TG_MAX_TAPS = 16;
 constexpr int TG_A_STAGE = TG_BM * TG_BK * 2;    // 16 KiB
 constexpr int TG_B_STAGE = 256 * TG_BK * 2;      // 32 KiB (BN <= 256)
@@ -36,7 +39,7 @@ constexpr int TG_EPI_WARPS = I2IT_EPI_WARPS;   // TG_EPI_GROUPS warps per TMEM l
 constexpr int TG_EPI_GROUPS = TG_EPI_WARPS / 4;
 constexpr int TG_EPI_RPW = 8 / TG_EPI_GROUPS;      // rounds per warp at BN = 256
 static_assert(TG_EPI_WARPS == 8, "epilogue warps: 8 (the 16-warp experiment of round 1 does not fit next to the 4 KB store boxes)");
-constexpr int TG_BAR_BYTES = 256;
+constexpr int TG_BAR_BYTES = 512;
 constexpr int TG_BIAS_BYTES = 2 * 256 * 4;       // per-tile bias slice, double-buffered like the accumulators
 // Epilogue store staging: each epilogue warp owns ONE TMA box = 32 rows x 64 output columns (128-byte rows, SWIZZLE_128B: the
 // 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)).  A thread holds one accumulator ROW, so direct stores touch 32
@@ -47,9 +50,9 @@ constexpr int TG_BIAS_BYTES = 2 * 256 * 4;       // per-tile bias slice, double-
 // through the box, added in place.
 constexpr int TG_OSTG_WARP = 32 * 128;
 constexpr int TG_OSTG_BYTES = TG_EPI_WARPS * TG_OSTG_WARP;
-// manual 1024-byte alignment slack of the dynamic smem base: 768 B are budgeted (a full 1 KB would put the CTA 256 B over the
+// manual 1024-byte alignment slack of the dynamic smem base: 512 B are budgeted (a full 1 KB would put the CTA over the
 // 227 KB limit) and the kernels trap with an error word if the runtime base needs more (it is 1 KB aligned in practice).
-constexpr int TG_ALIGN_PAD = 768;
+constexpr int TG_ALIGN_PAD = 512;
 constexpr int TG_SMEM = TG_STAGES * (TG_A_STAGE + TG_B_STAGE) + TG_BAR_BYTES + TG_BIAS_BYTES + TG_OSTG_BYTES + TG_ALIGN_PAD;
 constexpr int TG_THREADS = (TG_EPI_WARPS + 2) * 32;   // + TMA producer warp + MMA issuer warp
 constexpr int TG_ACC_COLS = 256;       // TMEM columns per accumulator stage
