@@ -59,12 +59,21 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
+        """Spawn the sampler and wait for its first row: nvidia-smi's own start-up (NVML init, ~0.5 s) must not fall inside the
+        timed region (it was seen to stretch a 10-step region by 25 % when it did)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 5.0:
+                time.sleep(0.05)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Rows from here on belong to the timed region."""
+        self.first = len(self.rows)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -73,8 +82,9 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.25)
         self.proc.terminate()
+        self.rows = self.rows[getattr(self, "first", 0):]
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -298,10 +308,12 @@ def main():
             dist.all_gather_into_tensor(gathered, wl.lat)              # the single collective: output latents over NVLink
 
     sampler = ClockSampler(local)
+    sampler.start()                      # before the warm-up: its start-up cost stays out of the timed region
     for _ in range(Wm):
+        flush.zero_()
         step()
     torch.cuda.synchronize()
-    sampler.start()
+    sampler.mark()
     ms_step, ms_mine = timed(step, K, 0, world, dist, flush)
     clocks = sampler.stop()
     value = world * B / (ms_step / 1e3)

@@ -920,6 +920,10 @@ Act Engine::group_norm(Plan& P, const Act& x, const NormW& nw, float eps, bool s
   static const int env_chunks = std::getenv("I2IT_GN_CHUNKS") ? atoi(std::getenv("I2IT_GN_CHUNKS")) : 512;
   const int rows = std::max(1, std::min(1024, env_thr) / vecs), threads = vecs * rows;
   const int chunks = std::max(1, std::min(env_chunks, ceil_div(HW, rows * 4)));
+  // gn_stats on a small tensor (every UNet map): at most 32 chunk partials, summed in gn_apply's prologue -> two launches per
+  // GroupNorm; gn_apply keeps its own (finer) pixel partition
+  const bool small_fallback = static_cast<long long>(HW) * C <= (4ll << 20);
+  const int schunks = small_fallback ? std::min(chunks, 32) : chunks, spix = ceil_div(HW, schunks);
   const int pix = ceil_div(HW, chunks);
   I2IT_CHECK(chunks <= 1024, "group_norm: too many chunks");
   auto partial = alloc_raw(P, std::max(static_cast<size_t>(x.N) * chunks * 64 * sizeof(float), static_cast<size_t>(x.N) * 4 * 32 * sizeof(double)* 2));
@@ -935,6 +939,7 @@ Act Engine::group_norm(Plan& P, const Act& x, const NormW& nw, float eps, bool s
   const float* b = nw.b;
   const double inv_count = 1.0 / (static_cast<double>(HW) * cg);
   const double2* d_part2 = nullptr;
+  const float* partf = nullptr;
   int nchunk = 0;
   if (x.gn && use_gnepi && x.gn->C == C && x.gn->images == N) {
     // the producer's epilogue already summed the tensor: reduce its per-slot partials (no pass over the tensor itself)
@@ -953,15 +958,16 @@ Act Engine::group_norm(Plan& P, const Act& x, const NormW& nw, float eps, bool s
     }, "gn_final_part", 0, 8.0 * gp.phases * N * gp.slots_per_image * per_row);
   } else {
     add_op(P, [=](cudaStream_t st) {
-      DISPATCH_T(dt, (launch_k(gn_stats_kernel<T>, dim3(chunks, N), dim3(threads), static_cast<size_t>(rows) * 2 * C * sizeof(float), st, 0,
-                               reinterpret_cast<const T*>(xp), ximg, ldx, C, HW, cg, pix, d_part)));
+      DISPATCH_T(dt, (launch_k(gn_stats_kernel<T>, dim3(schunks, N), dim3(threads), static_cast<size_t>(rows) * 2 * C * sizeof(float), st, 0,
+                               reinterpret_cast<const T*>(xp), ximg, ldx, C, HW, cg, spix, d_part)));
     }, "gn_stats", 0, 2.0 * N * HW * C);
-    add_op(P, [=](cudaStream_t st) { launch_k(gn_finalize_kernel, dim3(N), dim3(1024), 0, st, 0, d_part, chunks, inv_count, eps, d_stats); }, "gn_final");
+    if (small_fallback) { partf = d_part; nchunk = schunks; }
+    else add_op(P, [=](cudaStream_t st) { launch_k(gn_finalize_kernel, dim3(N), dim3(1024), 0, st, 0, d_part, schunks, inv_count, eps, d_stats); }, "gn_final");
   }
   add_op(P, [=](cudaStream_t st) {
     DISPATCH_T(dt, (launch_k(gn_apply_kernel<T>, dim3(chunks, N), dim3(threads), 0, st, 0,
                        reinterpret_cast<const T*>(xp), ximg, ldx, reinterpret_cast<T*>(yp), yimg, ldy, C, HW, cg, pix,
-                       d_stats, g, b, isilu, d_part2, nchunk, inv_count, eps)));
+                       d_stats, g, b, isilu, d_part2, nchunk, inv_count, eps, partf)));
   }, "gn_apply", 0, 4.0 * N * HW * C);
   return y;     // (y carries no statistics: it is a different tensor)
 }

@@ -150,7 +150,7 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, long long ximg, int ldx
                                 int ldy, int C, int HW, int cg, int pix_per_cta, const float* __restrict__ stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
                                 const double2* __restrict__ part2 = nullptr, int nchunk = 0, double inv_count = 0.0,
-                                float eps = 0.f) {
+                                float eps = 0.f, const float* __restrict__ partf = nullptr) {
   pdl_sync();
   const int vecs = C >> 3;
   const int vx = threadIdx.x % vecs, vy = threadIdx.x / vecs, rows = blockDim.x / vecs;
@@ -164,11 +164,19 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, long long ximg, int ldx
     const int c = vx * 8 + i, g = c / cg;
     if (g != gprev) {
       gprev = g;
-      if (part2) {             // statistics came from the producing GEMM's epilogue: fold the last (<= 4) chunk partials here
+      if (part2 || partf) {    // last reduction level folded in here: <= 4 double chunk partials (statistics taken in the producing
+                               // GEMM's epilogue) or <= 32 float chunk partials (gn_stats on a small tensor): no finalize launch
         double a = 0.0, b = 0.0;
-        for (int k = 0; k < nchunk; ++k) {
-          const double2 v = part2[(static_cast<long long>(n) * nchunk + k) * 32 + g];
-          a += v.x; b += v.y;
+        if (part2) {
+          for (int k = 0; k < nchunk; ++k) {
+            const double2 v = part2[(static_cast<long long>(n) * nchunk + k) * 32 + g];
+            a += v.x; b += v.y;
+          }
+        } else {
+          for (int k = 0; k < nchunk; ++k) {
+            const float2 v = reinterpret_cast<const float2*>(partf)[(static_cast<long long>(n) * nchunk + k) * 32 + g];
+            a += static_cast<double>(v.x); b += static_cast<double>(v.y);
+          }
         }
         const double m = a * inv_count;
         double var = b * inv_count - m * m;
