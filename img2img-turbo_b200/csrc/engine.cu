@@ -116,7 +116,10 @@ Engine::Engine(const i2it_config& c) : cfg(c), dtype(c.dtype) {
   I2IT_CUDA(cudaFuncSetAttribute(tapgemm_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
   I2IT_CUDA(cudaFuncSetAttribute(flash_attn_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
   I2IT_CUDA(cudaFuncSetAttribute(flash_attn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+  I2IT_CUDA(cudaFuncSetAttribute(flash_attn_v1_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+  I2IT_CUDA(cudaFuncSetAttribute(flash_attn_v1_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
   use_flash = std::getenv("I2IT_NO_FLASH") == nullptr;
+  flash_v1 = std::getenv("I2IT_FLASH_V1") != nullptr;       // round-1 softmax scheme (A/B)
   use_pair = std::getenv("I2IT_NO_PAIR") == nullptr;
   use_pdl = std::getenv("I2IT_PDL") != nullptr;     // programmatic dependent launch: measured neutral (1 CTA/SM kernels cannot co-reside), opt-in
 #ifdef I2IT_TRACE_BUILD
@@ -124,6 +127,7 @@ Engine::Engine(const i2it_config& c) : cfg(c), dtype(c.dtype) {
 #endif
   use_tmaout = std::getenv("I2IT_NO_TMAOUT") == nullptr;   // TMA-store epilogue (per-thread stores otherwise)
   use_gnepi = std::getenv("I2IT_NO_GNEPI") == nullptr;     // GroupNorm statistics in the producing GEMM's epilogue
+  use_splitk = std::getenv("I2IT_NO_SPLITK") == nullptr;   // split-K for the 8x8 1280-channel convs
   pair_min_tiles = std::getenv("I2IT_PAIR_MIN_TILES") ? atoll(std::getenv("I2IT_PAIR_MIN_TILES")) : 2ll * num_sms;
   use_idres = std::getenv("I2IT_NO_IDRES") == nullptr;
   use_halo = std::getenv("I2IT_NO_HALO") == nullptr;   // 3x3 convs: one halo tile per k-chunk instead of nine shifted A boxes
@@ -571,9 +575,9 @@ void Engine::launch_gemm(Plan& P, const TmapSpec& sa, TmapSpec sb, const TapGemm
     if (p.tap_kc[t] == 0) p.tap_kc[t] = p.kchunks;          // single-source callers only set kchunks
   if (p.nprim == 0) p.nprim = p.num_taps;
   const long long m_tiles = 1ll * p.tdim[0] * p.tdim[1] * p.tdim[2] * p.tdim[3];
-  const long long total_tiles = m_tiles * p.n_tiles;
+  const long long total_tiles = m_tiles * p.n_tiles * (p.ksplit > 1 ? p.ksplit : 1);
   // CTA-pair kernel: weights/B shared by every M tile (no per-tile B batch coordinates), enough tiles to fill the chip twice
-  const bool pair = use_pair && p.b_mul[0] == 0 && p.b_mul[1] == 0 && p.b_mul[2] == 0 && (p.BN % 32) == 0 &&
+  const bool pair = use_pair && p.ksplit <= 1 && p.b_mul[0] == 0 && p.b_mul[1] == 0 && p.b_mul[2] == 0 && (p.BN % 32) == 0 &&
                     total_tiles >= pair_min_tiles && m_tiles >= 2;
   TmapSpec sb2 = sb2p ? *sb2p : sb;
   if (pair) { sb.box[1] = p.BN / 2; sb2.box[1] = p.BN / 2; p.idesc = make_idesc2(dtype, p.BN); }
@@ -850,6 +854,33 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o_in) {
     }
   }
 
+  // split-K for the 8x8 / 1280-channel convs (M = 64 rows per image): with K = 11.5k..23k and 4 m-tiles per batch of 8 the
+  // launch had 80-108 weight-bandwidth-bound CTAs; five K ranges per tile write fp32 partials that splitk_reduce sums in a fixed
+  // order.  The decision and the ranges depend on the layer only (never on the batch): batch-invariant bits.
+  const bool splitk = use_splitk && !sub && k == 3 && o.stride == 1 && !o.to_io_out_nchw && !o.out_fp32 && o.act == TG_ACT_NONE &&
+                      x.H * x.W <= 64 && p.kchunks * taps >= 180 && p.kchunks % 5 == 0 && gemm_n >= 640 && gemm_n % 8 == 0 && !o.out;
+  std::shared_ptr<void> sk_hold;
+  const Act* sk_res = nullptr;
+  const float* sk_bias = nullptr;
+  if (splitk) {
+    const int S = 5;                      // kchunks is 20 or 40 here: equal shares
+    const long long Mrows = 1ll * x.N * Ho * Wo;
+    sk_hold = alloc_raw(P, static_cast<size_t>(S) * Mrows * gemm_n * sizeof(float));
+    p.ksplit = S;
+    p.kc_per = ceil_div(p.kchunks, S);
+    p.split_ostride = Mrows * gemm_n;
+    p.out = sk_hold.get();
+    p.out_fp32 = 1;
+    p.ostride[0] = gemm_n; p.ostride[1] = 1ll * Wo * gemm_n; p.ostride[2] = 1ll * Ho * Wo * gemm_n; p.ostride[3] = 0;
+    sk_res = o.res; sk_bias = (p.bias_mode == TG_BIAS_COL) ? p.bias : nullptr;
+    p.res = nullptr; p.bias = nullptr; p.bias_mode = TG_BIAS_NONE;
+    p.gn_part = nullptr; out.gn = nullptr;
+    p.BN = 256;
+    p.n_tiles = ceil_div(gemm_n, p.BN);
+    sb.box[1] = p.BN;
+    p.idesc = make_idesc(dtype, p.BN);
+  }
+
   TmapSpec sa2, sb2;
   double k2 = 0;
   if (o.x2) {
@@ -894,6 +925,18 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o_in) {
     sh.box[1] = TG2_HALO_W; sh.box[2] = TG2_HALO_H; sh.box[3] = 1;
     launch_gemm(P, sa, sb, p, o.to_io_out_nchw, kind, k_valid, bytes, o.x2 ? &sa2 : nullptr, o.x2 ? &sb2 : nullptr,
                 want_halo ? &sh : nullptr);
+  }
+  if (splitk) {
+    const float* part = static_cast<const float*>(sk_hold.get());
+    const long long Mrows = 1ll * x.N * Ho * Wo, total = Mrows * (gemm_n / 8), sstride = p.split_ostride;
+    const uint16_t* rp = sk_res ? sk_res->p : nullptr;
+    uint16_t* op = out.p;
+    const int ldr = sk_res ? sk_res->ld : 0, ldo2 = out.ld, S = p.ksplit, dt = dtype, Nn = gemm_n;
+    const float* bb = sk_bias;
+    add_op(P, [=](cudaStream_t st) {
+      DISPATCH_T(dt, (launch_k(splitk_reduce_kernel<T>, dim3(ceil_div(total, 256)), dim3(256), 0, st, 0, part, S, sstride, bb,
+                               reinterpret_cast<const T*>(rp), ldr, reinterpret_cast<T*>(op), ldo2, Nn, total)));
+    }, "splitk_reduce", 0, 4.0 * S * Mrows * gemm_n + 4.0 * Mrows * gemm_n);
   }
   return out;
 }
@@ -1219,8 +1262,10 @@ Act Engine::flash_attention(Plan& P, const Act& q, const Act& k, const Act& vt, 
   const int grid = fp.q_tiles * heads * B, dt = dtype;
   char shp[96];
   snprintf(shp, sizeof shp, "B=%d h=%d Nq=%d Nk=%d d=%d", B, heads, Nq, Nk, d);
+  const bool v1 = flash_v1;
   add_op(P, [=](cudaStream_t st) {
-    DISPATCH_T(dt, (launch_k(flash_attn_kernel<T>, dim3(grid), dim3(FA_THREADS), FA_SMEM, st, 0, tq, tk, tv, fp)));
+    if (v1) { DISPATCH_T(dt, (launch_k(flash_attn_v1_kernel<T>, dim3(grid), dim3(FA_THREADS), FA_SMEM, st, 0, tq, tk, tv, fp))); }
+    else { DISPATCH_T(dt, (launch_k(flash_attn_kernel<T>, dim3(grid), dim3(FA_THREADS), FA_SMEM, st, 0, tq, tk, tv, fp))); }
   }, "flash_attn", 4.0 * B * heads * Nq * Nk * d, 2.0 * (2.0 * B * Nq * C + 2.0 * kv_batch * Nk * C), shp);
   return out;
 }

@@ -14,6 +14,7 @@
 #include "prep.cuh"
 #include "tapgemm.cuh"
 #include "flash.cuh"
+#include "flash_v1.cuh"
 #include "tapgemm2.cuh"
 
 namespace i2it {
@@ -200,7 +201,7 @@ class Engine {
                 int kv_batch);
   Act flash_attention(Plan& P, const Act& q, const Act& k, const Act& vt, int B, int Nq, int Nk, int heads, int kv_batch,
                       bool causal = false);
-  bool use_flash = true;
+  bool use_flash = true, flash_v1 = false;
 
   // ---- weights ----
   bool has(const std::string& key) const;
@@ -241,7 +242,7 @@ class Engine {
   void launch_gemm(Plan& P, const TmapSpec& sa, TmapSpec sb, const TapGemmParams& p, bool out_from_io, const char* kind,
                    double k_valid, double bytes, const TmapSpec* sa2 = nullptr, const TmapSpec* sb2 = nullptr,
                    const TmapSpec* shalo = nullptr);
-  bool use_pair = true, use_halo = true, use_idres = true, use_pdl = false, trace_on = false, use_tmaout = true, use_gnepi = true;
+  bool use_pair = true, use_halo = true, use_idres = true, use_pdl = false, trace_on = false, use_tmaout = true, use_gnepi = true, use_splitk = true;
   bool tma_eligible(const TapGemmParams& p, bool out_from_io) const;
   long long pair_min_tiles = 296;   // CTA-pair kernel from two waves of tiles upwards (tunable: I2IT_PAIR_MIN_TILES)
   std::string profile_json(int reps, cudaStream_t st);

@@ -9,8 +9,11 @@
 //   warp 5 lane 0 : MMA issuer     S_j = Q K_j^T (4 x tcgen05.mma M128 N64 K16) -> TMEM S buffer j&1
 //                                  PV_j = P_j V_j  (4 x tcgen05.mma, A = P_j staged in swizzled smem) -> TMEM cols [128,192)
 //                                  QK_{j+1} is issued as soon as the softmax warps have pulled S_j out of TMEM
-//   warps 0..3    : one Q row per thread: online softmax in fp32 (exp2, running max / sum), P_j -> bf16/fp16 smem tile,
-//                   O accumulated in registers  (o = o*alpha + PV_j),  final O / l written once
+//   warps 0..3    : one Q row per thread: S_j is pulled out of TMEM ONCE (64 registers), online softmax in fp32 with a LAZY
+//                   reference maximum, P_j -> bf16/fp16 smem tile; O stays in TMEM (PV accumulates across KV steps) and is only
+//                   rescaled (tcgen05.ld -> mul -> tcgen05.st) when a row's maximum grows by more than 2^8; final O / l written once.
+//                   Round 1 read S twice and the PV tile once per step: 96 KB of TMEM reads per step at 64 B/clk/SM made the
+//                   kernel TMEM-read bound (25 % tensor pipe); this version reads 32 KB per step.
 // 2 CTAs per SM (80 KB smem, 256 TMEM columns each: S double-buffered + PV) so one CTA's MMAs overlap the other's exponentials.
 #pragma once
 #include "tapgemm.cuh"
@@ -44,6 +47,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -149,7 +163,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       if (elect_one()) {
         const uint64_t vdesc = umma_desc_sw128(sKV + s * FA_KV_STAGE + FA_BN * FA_D * 2);
 #pragma unroll
-        for (int k = 0; k < FA_BN / 16; ++k) tc_mma_f16(tPV, pdesc + 2 * k, vdesc + 2 * k, p.idesc, k > 0 ? 1u : 0u);
+        for (int k = 0; k < FA_BN / 16; ++k)                 // O accumulates in TMEM across the KV steps
+          tc_mma_f16(tPV, pdesc + 2 * k, vdesc + 2 * k, p.idesc, (j > 0 || k > 0) ? 1u : 0u);
         tc_commit(pv_full);
         tc_commit(kv_empty(s));                     // K_j and V_j are free once everything issued so far retires
       }
@@ -159,75 +174,85 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     // ---------------- softmax / output warps: thread = Q row ----------------
     const int row = warp * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-    float o[FA_D];
-#pragma unroll
-    for (int i = 0; i < FA_D; ++i) o[i] = 0.f;
-    float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
+    const int qpos = qt * FA_BM + row;
+    const int klim = p.causal ? min(p.Nk, qpos + 1) : p.Nk;     // keys [0, klim) are visible to this row
+    const float sc = p.scale_log2e;
+    constexpr float TAU = 8.0f;                                  // lazy rescale: P <= 2^8 relative to the reference maximum
+    float m = -INFINITY, l = 0.f;                                // m: reference maximum (raw logit units) of this row
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(s_full(j & 1), (j >> 1) & 1, p.err, 16);
       tc_fence_after();
       const uint32_t tS = tS0 + 64 * (j & 1);
       const int kbase = j * FA_BN;
-      const int qpos = qt * FA_BM + row;
       // element-wise masking only where needed (warp-uniform): the last KV tile, or causal tiles that reach this warp's diagonal
       const bool ragged = (kbase + FA_BN > p.Nk) || (p.causal && kbase + FA_BN - 1 > qt * FA_BM + warp * 32);
-      const int klim = p.causal ? min(p.Nk, qpos + 1) : p.Nk;   // keys [0, klim) are visible to this row
-      const float sc = p.scale_log2e;
-      // pass 1: row max of the RAW logits (scale > 0 keeps the order; one FMNMX per element)
-      float mx = -INFINITY;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t raw[32];
-        tc_ld32(tS + lane_off + half * 32, raw);
+      // S_j leaves TMEM once: 64 fp32 logits per row in registers; the buffer goes back to the MMA warp right away
+      uint32_t raw[64];
+      {
+        uint32_t (&r0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&raw[0]);
+        uint32_t (&r1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&raw[32]);
+        tc_ld32(tS + lane_off, r0);
+        tc_ld32(tS + lane_off + 32, r1);
         tc_wait_ld();
-        if (ragged) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (kbase + half * 32 + i < klim) mx = fmaxf(mx, __uint_as_float(raw[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
-        }
       }
-      const float m_new = fmaxf(m, mx);                    // m, m_new in raw (unscaled) units
-      const float alpha = fast_exp2((m - m_new) * sc);     // first tile: exp2(-inf) = 0
-      const float neg_ms = -m_new * sc;
-      // fold in PV_{j-1} before P_{j-1}'s smem tile is overwritten
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free(j & 1));
+      float mx = -INFINITY;
+      if (ragged) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (kbase + i < klim) mx = fmaxf(mx, __uint_as_float(raw[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+      }
+      // PV_{j-1} must have landed before O is rescaled and before P_{j-1}'s smem tile is overwritten
       if (j > 0) {
         mbar_wait(pv_full, (j - 1) & 1, p.err, 17);
         tc_fence_after();
+      }
+      const bool grow = (fmaxf(m, mx) - m) * sc > TAU;          // first tile: m = -inf -> true
+      if (j == 0) {
+        m = mx;
+      } else if (__any_sync(0xffffffffu, grow)) {
+        // some row of this warp outgrew its reference maximum: rescale the warp's 32 O rows in TMEM (factor 1 for the others)
+        const float m_new = grow ? fmaxf(m, mx) : m;
+        const float factor = fast_exp2((m - m_new) * sc);
+        uint32_t o[32];
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          uint32_t raw[32];
-          tc_ld32(tPV + lane_off + half * 32, raw);
+          tc_ld32(tPV + lane_off + half * 32, o);
           tc_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[half * 32 + i] = o[half * 32 + i] * alpha_prev + __uint_as_float(raw[i]);
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+          tc_st32(tPV + lane_off + half * 32, o);
         }
+        tc_wait_st();
+        l *= factor;
+        m = m_new;
       }
-      // pass 2: p = exp2(s*scale - m*scale) (one FFMA + one MUFU per element), fp32 row sum of the unrounded p (as
-      // FlashAttention does), pack to 16 bit, write the swizzled K-major P tile
+      const float neg_ms = -m * sc;
+      // p = exp2(s*scale - m*scale) (one FFMA + one MUFU per element), fp32 row sum of the unrounded p, pack to 16 bit, write the
+      // swizzled K-major P tile
       float psum = 0.f;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        uint32_t raw[32];
-        tc_ld32(tS + lane_off + half * 32, raw);
-        tc_wait_ld();
         uint32_t pk[16];
         if (ragged) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int k0 = kbase + half * 32 + 2 * i;
-            const float p0 = (k0 < klim) ? fast_exp2(fmaf(__uint_as_float(raw[2 * i]), sc, neg_ms)) : 0.f;
-            const float p1 = (k0 + 1 < klim) ? fast_exp2(fmaf(__uint_as_float(raw[2 * i + 1]), sc, neg_ms)) : 0.f;
+            const float p0 = (k0 < klim) ? fast_exp2(fmaf(__uint_as_float(raw[half * 32 + 2 * i]), sc, neg_ms)) : 0.f;
+            const float p1 = (k0 + 1 < klim) ? fast_exp2(fmaf(__uint_as_float(raw[half * 32 + 2 * i + 1]), sc, neg_ms)) : 0.f;
             psum += p0 + p1;
             pk[i] = Elem<T>::pack(p0, p1);
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(raw[2 * i]), sc, neg_ms));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(raw[2 * i + 1]), sc, neg_ms));
+            const float p0 = fast_exp2(fmaf(__uint_as_float(raw[half * 32 + 2 * i]), sc, neg_ms));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(raw[half * 32 + 2 * i + 1]), sc, neg_ms));
             psum += p0 + p1;
             pk[i] = Elem<T>::pack(p0, p1);
           }
@@ -238,38 +263,34 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           sts16(sP + row * 128 + ((gg ^ (row & 7)) << 4), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
         }
       }
-      l = l * alpha + psum;
-      m = m_new;
-      alpha_prev = alpha;
-      // S_j fully consumed -> the MMA warp may overwrite S with QK_{j+1};  P_j visible to the async proxy -> PV_j may start
+      l += psum;
+      // P_j visible to the async proxy (and any O rescale complete) -> PV_j may start
       tc_fence_before();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) { mbar_arrive(s_free(j & 1)); mbar_arrive(p_full); }
+      if (lane == 0) mbar_arrive(p_full);
     }
-    // last PV
+    // last PV, then the only read of O
     mbar_wait(pv_full, (nkv - 1) & 1, p.err, 18);
     tc_fence_after();
+    const int q = qt * FA_BM + row;
+    const float inv = 1.0f / l;
+    T* optr = reinterpret_cast<T*>(p.out) + (static_cast<long long>(b) * p.Nq + q) * p.ldo + h * FA_D;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      uint32_t raw[32];
-      tc_ld32(tPV + lane_off + half * 32, raw);
+      uint32_t o[32];
+      tc_ld32(tPV + lane_off + half * 32, o);
       tc_wait_ld();
+      if (q < p.Nq) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[half * 32 + i] = o[half * 32 + i] * alpha_prev + __uint_as_float(raw[i]);
-    }
-    const int q = qt * FA_BM + row;
-    if (q < p.Nq) {
-      const float inv = 1.0f / l;
-      T* optr = reinterpret_cast<T*>(p.out) + (static_cast<long long>(b) * p.Nq + q) * p.ldo + h * FA_D;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        uint4 u;
-        u.x = Elem<T>::pack(o[8 * g] * inv, o[8 * g + 1] * inv);
-        u.y = Elem<T>::pack(o[8 * g + 2] * inv, o[8 * g + 3] * inv);
-        u.z = Elem<T>::pack(o[8 * g + 4] * inv, o[8 * g + 5] * inv);
-        u.w = Elem<T>::pack(o[8 * g + 6] * inv, o[8 * g + 7] * inv);
-        st16(optr + 8 * g, u);
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = Elem<T>::pack(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
+          u.y = Elem<T>::pack(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
+          u.z = Elem<T>::pack(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
+          u.w = Elem<T>::pack(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
+          st16(optr + half * 32 + 8 * g, u);
+        }
       }
     }
   }

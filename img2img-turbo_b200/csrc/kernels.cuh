@@ -591,6 +591,33 @@ __global__ void pad_copy_kernel(const T* __restrict__ x, int ldx, T* __restrict_
   st16(y + ((n * H2 + oy) * W2 + ox) * C + v * 8, u);
 }
 
+// split-K epilogue: out[r][c] = round( sum_s part[s][r][c] + bias[c] + res[r][c] ), partials summed in index order (reproducible)
+template <typename T>
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int S, long long split_stride, const float* __restrict__ bias,
+                                     const T* __restrict__ res, int ldr, T* __restrict__ out, int ldo, int N, long long total /* rows*N/8 */) {
+  pdl_sync();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int vecs = N >> 3;
+  const long long r = i / vecs;
+  const int c0 = static_cast<int>(i % vecs) * 8;
+  float v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = bias ? bias[c0 + k] : 0.f;
+  for (int s = 0; s < S; ++s) {
+    const float4* p4 = reinterpret_cast<const float4*>(part + s * split_stride + r * N + c0);
+    const float4 a = p4[0], b = p4[1];
+    v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+  }
+  if (res) {
+    const uint4 u = ld_nc16(res + r * ldr + c0);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 f = Elem<T>::unpack(w[k]); v[2 * k] += f.x; v[2 * k + 1] += f.y; }
+  }
+  st16(out + r * ldo + c0, make_uint4(Elem<T>::pack(v[0], v[1]), Elem<T>::pack(v[2], v[3]), Elem<T>::pack(v[4], v[5]), Elem<T>::pack(v[6], v[7])));
+}
+
 // strided 2-D copy of 16-byte vectors: rows x (C/8) vectors (torch.cat along channels)
 template <typename T>
 __global__ void copy2d_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int C, long long total) {

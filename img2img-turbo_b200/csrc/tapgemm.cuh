@@ -95,6 +95,10 @@ struct TapGemmParams {
   // GroupNorm statistics of the OUTPUT tensor, taken from the staged (rounded) tile: per 32-row slot and per `gn_red` columns,
   // (sum, sum of squares) -> gn_part[(slot0 + m_tile*4 + quarter) * (N/gn_red) + col/gn_red][2]; nullptr = off
   float* gn_part;
+  // split-K (1-CTA kernel only): the primary taps' k-chunks are divided over `ksplit` tiles that write fp32 partials
+  // `split_ostride` elements apart (splitk_reduce_kernel sums them in a fixed order); secondary taps go with split 0
+  int ksplit, kc_per;
+  long long split_ostride;
   int gn_red, gn_slot0, gn_mtiles;   // gn_mtiles: m-tiles of the launch (the pair kernel's odd tail tile has no slot)
   unsigned long long* trace;   // optional (I2IT_TRACE=1): 16 %clock64 stamps per CTA at the phase boundaries, else nullptr
 };
@@ -226,7 +230,7 @@ __device__ __forceinline__ void tg_stamp(const TapGemmParams& p, int slot) {
 }
 
 struct TileCoord {
-  int nt, t[4];
+  int nt, t[4], split;
 };
 __device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int tile) {
   TileCoord c;
@@ -235,7 +239,8 @@ __device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int til
   c.t[0] = r % p.tdim[0]; r /= p.tdim[0];
   c.t[1] = r % p.tdim[1]; r /= p.tdim[1];
   c.t[2] = r % p.tdim[2]; r /= p.tdim[2];
-  c.t[3] = r;
+  c.t[3] = r % p.tdim[3];
+  c.split = r / p.tdim[3];                       // 0 unless ksplit > 1 (slowest index)
   return c;
 }
 
@@ -346,7 +351,7 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const CUte
   const int g1 = c.t[0] * p.box[0] + j1, g2 = c.t[1] * p.box[1] + j2, g3 = c.t[2] * p.box[2] + j3,
             g4 = c.t[3] * p.box[3] + j4;
   const bool row_ok = (g1 < p.ext[0]) && (g2 < p.ext[1]) && (g3 < p.ext[2]) && (g4 < p.ext[3]);
-  const long long obase = g1 * p.ostride[0] + g2 * p.ostride[1] + g3 * p.ostride[2] + g4 * p.ostride[3];
+  const long long obase = g1 * p.ostride[0] + g2 * p.ostride[1] + g3 * p.ostride[2] + g4 * p.ostride[3] + c.split * p.split_ostride;
   const long long rbase = g1 * p.rstride[0] + g2 * p.rstride[1] + g3 * p.rstride[2] + g4 * p.rstride[3];
   const float rbias = (p.bias_mode == TG_BIAS_ROW && row_ok) ? p.bias[g1] : 0.0f;
   const int n0 = c.nt * p.BN;
@@ -587,9 +592,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) tg_stamp(p, 0);
-  const int total_tiles = p.n_tiles * p.tdim[0] * p.tdim[1] * p.tdim[2] * p.tdim[3];
-  int steps = 0;
+  const int nsplit = p.ksplit > 1 ? p.ksplit : 1;
+  const int total_tiles = p.n_tiles * p.tdim[0] * p.tdim[1] * p.tdim[2] * p.tdim[3] * nsplit;
+  int steps = 0, sec_steps = 0;
   for (int t = 0; t < p.num_taps; ++t) steps += p.tap_kc[t];
+  for (int t = p.nprim; t < p.num_taps; ++t) sec_steps += p.tap_kc[t];
 
   if (warp == TG_EPI_WARPS && lane == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -637,10 +644,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (++stage == NS) { stage = 0; phase ^= 1; }
       };
-      for (int kc = 0; kc < p.kchunks; ++kc)
+      const int kc0 = nsplit > 1 ? c.split * p.kc_per : 0, kc1 = nsplit > 1 ? min(p.kchunks, kc0 + p.kc_per) : p.kchunks;
+      for (int kc = kc0; kc < kc1; ++kc)
         for (int t = 0; t < p.nprim; ++t) load_step(t, kc);
-      for (int t = p.nprim; t < p.num_taps; ++t)
-        for (int kc = 0; kc < p.tap_kc[t]; ++kc) load_step(t, kc);
+      if (c.split == 0)
+        for (int t = p.nprim; t < p.num_taps; ++t)
+          for (int kc = 0; kc < p.tap_kc[t]; ++kc) load_step(t, kc);
       if (tile == static_cast<int>(blockIdx.x) && lane == 0) tg_stamp(p, 2);   // first tile's loads all issued
     }
     if (lane == 0) tg_stamp(p, 3);
@@ -652,7 +661,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tempty_bar(acc), aphase ^ 1, p.err, 2);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * TG_ACC_COLS;
-      for (int s = 0; s < steps; ++s) {
+      int tsteps = steps;
+      if (nsplit > 1) {                                                         // this tile's share of the K loop
+        const int split = tile / (total_tiles / nsplit);
+        const int kc0 = split * p.kc_per, kc1 = min(p.kchunks, kc0 + p.kc_per);
+        tsteps = (kc1 - kc0) * p.nprim + (split == 0 ? sec_steps : 0);
+      }
+      for (int s = 0; s < tsteps; ++s) {
         mbar_wait(full_bar(stage), phase, p.err, 3);
         tc_fence_after();
         if (iter == 0 && s == 0 && lane == 0) tg_stamp(p, 4);                   // first operands landed
@@ -663,7 +678,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < TG_BK / 16; ++k)
             tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (s > 0 || k > 0) ? 1u : 0u);
           tc_commit(empty_bar(stage));               // frees the smem slot when these MMAs retire
-          if (s == steps - 1) tc_commit(tfull_bar(acc));   // accumulator complete -> epilogue
+          if (s == tsteps - 1) tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
         }
         __syncwarp();
         if (++stage == NS) { stage = 0; phase ^= 1; }

@@ -151,6 +151,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     c.t[1] = r % p.tdim[1]; r /= p.tdim[1];
     c.t[2] = r % p.tdim[2]; r /= p.tdim[2];
     c.t[3] = r;                               // may exceed tdim[3] for the odd tail: rows then fail the extent check
+    c.split = 0;                              // split-K is a 1-CTA-kernel feature
     return c;
   };
 
