@@ -128,6 +128,7 @@ Engine::Engine(const i2it_config& c) : cfg(c), dtype(c.dtype) {
   use_tmaout = std::getenv("I2IT_NO_TMAOUT") == nullptr;   // TMA-store epilogue (per-thread stores otherwise)
   use_gnepi = std::getenv("I2IT_NO_GNEPI") == nullptr;     // GroupNorm statistics in the producing GEMM's epilogue
   use_splitk = std::getenv("I2IT_NO_SPLITK") == nullptr;   // split-K for the 8x8 1280-channel convs
+  use_catfuse = std::getenv("I2IT_NO_CATFUSE") == nullptr; // UNet skip concatenations written in place (no copy kernels)
   pair_min_tiles = std::getenv("I2IT_PAIR_MIN_TILES") ? atoll(std::getenv("I2IT_PAIR_MIN_TILES")) : 2ll * num_sms;
   use_idres = std::getenv("I2IT_NO_IDRES") == nullptr;
   use_halo = std::getenv("I2IT_NO_HALO") == nullptr;   // 3x3 convs: one halo tile per k-chunk instead of nine shifted A boxes
@@ -858,7 +859,7 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o_in) {
   // launch had 80-108 weight-bandwidth-bound CTAs; five K ranges per tile write fp32 partials that splitk_reduce sums in a fixed
   // order.  The decision and the ranges depend on the layer only (never on the batch): batch-invariant bits.
   const bool splitk = use_splitk && !sub && k == 3 && o.stride == 1 && !o.to_io_out_nchw && !o.out_fp32 && o.act == TG_ACT_NONE &&
-                      x.H * x.W <= 64 && p.kchunks * taps >= 180 && p.kchunks % 5 == 0 && gemm_n >= 640 && gemm_n % 8 == 0 && !o.out;
+                      x.H * x.W <= 64 && p.kchunks * taps >= 180 && p.kchunks % 5 == 0 && gemm_n >= 640 && gemm_n % 8 == 0;
   std::shared_ptr<void> sk_hold;
   const Act* sk_res = nullptr;
   const float* sk_bias = nullptr;
@@ -941,14 +942,15 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o_in) {
   return out;
 }
 
-Act Engine::linear(Plan& P, const Act& x, const PW& w, const Act* res, int act, bool gn_out) {
+Act Engine::linear(Plan& P, const Act& x, const PW& w, const Act* res, int act, bool gn_out, const Act* out) {
   ConvOpts o;
   o.ksize = 1;
   o.act = act;
   o.gn_out = gn_out;
   o.gn_rows_per_image = static_cast<long long>(x.H) * x.W;
-  Act xr = x.as_rows(), rr;
+  Act xr = x.as_rows(), rr, orows;
   if (res) { rr = res->as_rows(); o.res = &rr; }
+  if (out) { orows = out->as_rows(); o.out = &orows; }
   Act y = conv(P, xr, w, o);
   y.N = x.N; y.H = x.H; y.W = x.W;
   return y;

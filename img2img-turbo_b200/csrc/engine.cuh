@@ -187,7 +187,8 @@ class Engine {
   Act alloc_act(Plan& P, int N, int H, int W, int C, int ld = 0, bool zero_persistent = false);
   std::shared_ptr<void> alloc_raw(Plan& P, size_t bytes);
   Act conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o);
-  Act linear(Plan& P, const Act& x, const PW& w, const Act* res = nullptr, int act = TG_ACT_NONE, bool gn_out = false);
+  Act linear(Plan& P, const Act& x, const PW& w, const Act* res = nullptr, int act = TG_ACT_NONE, bool gn_out = false,
+             const Act* out = nullptr);
   Act group_norm(Plan& P, const Act& x, const NormW& nw, float eps, bool silu);
   Act layer_norm(Plan& P, const Act& x, const NormW& nw, bool to_io_out = false);
   Act upsample2x(Plan& P, const Act& x) { return upsample_to(P, x, 2 * x.H, 2 * x.W); }
@@ -228,8 +229,10 @@ class Engine {
   Act vae_resnet(Plan& P, const std::string& p, const Act& x, const Act* skip = nullptr, const PW* skip_w = nullptr,
                  bool gn_next = true);
   Act vae_attn(Plan& P, const std::string& p, const Act& x);
-  Act unet_resnet(Plan& P, const std::string& p, const Act& x, bool gn_next = false);
-  Act unet_xformer(Plan& P, const std::string& p, const Act& x, int heads, int text_batch, bool gn_next = false);
+  // `out`: write the block's output into this view (a channel slice of a pre-allocated concat buffer) instead of a new tensor
+  Act unet_resnet(Plan& P, const std::string& p, const Act& x, bool gn_next = false, const Act* out = nullptr);
+  Act unet_xformer(Plan& P, const std::string& p, const Act& x, int heads, int text_batch, bool gn_next = false,
+                   const Act* out = nullptr);
   void mark(Plan& P, const std::string& name, const Act& a) { if (cfg.keep_stages) P.stages[name] = a; }
 
   template <typename F> void add_op(Plan& P, F&& f, const char* kind = "misc", double flops = 0, double bytes = 0,
@@ -242,7 +245,7 @@ class Engine {
   void launch_gemm(Plan& P, const TmapSpec& sa, TmapSpec sb, const TapGemmParams& p, bool out_from_io, const char* kind,
                    double k_valid, double bytes, const TmapSpec* sa2 = nullptr, const TmapSpec* sb2 = nullptr,
                    const TmapSpec* shalo = nullptr);
-  bool use_pair = true, use_halo = true, use_idres = true, use_pdl = false, trace_on = false, use_tmaout = true, use_gnepi = true, use_splitk = true;
+  bool use_pair = true, use_halo = true, use_idres = true, use_pdl = false, trace_on = false, use_tmaout = true, use_gnepi = true, use_splitk = true, use_catfuse = true;
   bool tma_eligible(const TapGemmParams& p, bool out_from_io) const;
   long long pair_min_tiles = 296;   // CTA-pair kernel from two waves of tiles upwards (tunable: I2IT_PAIR_MIN_TILES)
   std::string profile_json(int reps, cudaStream_t st);

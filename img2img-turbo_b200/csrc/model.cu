@@ -158,7 +158,7 @@ void Engine::build_vae_decoder(Plan& P, const std::string& vp, const Act& dec_in
 }
 
 // ------------------------------------------------------------------------------------------ UNet
-Act Engine::unet_resnet(Plan& P, const std::string& p, const Act& x, bool gn_next) {
+Act Engine::unet_resnet(Plan& P, const std::string& p, const Act& x, bool gn_next, const Act* out) {
   Act h = group_norm(P, x, norm(p + ".norm1"), 1e-5f, true);
   // t == 999 always: time_emb_proj(silu(emb)) is a per-channel constant -> part of conv1's bias
   ConvOpts o1; o1.gn_out = true;
@@ -166,6 +166,7 @@ Act Engine::unet_resnet(Plan& P, const std::string& p, const Act& x, bool gn_nex
   h = group_norm(P, h, norm(p + ".norm2"), 1e-5f, true);
   ConvOpts o;
   o.gn_out = gn_next;
+  o.out = out;
   if (has(p + ".conv_shortcut.weight")) {
     PW wsc = prep(p + ".conv_shortcut", {p + ".conv_shortcut"});
     PW w2 = prep(p + ".conv2+sc", {p + ".conv2"}, false, 1.f, raw(p + ".conv_shortcut", "bias").d);
@@ -176,7 +177,7 @@ Act Engine::unet_resnet(Plan& P, const std::string& p, const Act& x, bool gn_nex
   return conv(P, h, prep(p + ".conv2", {p + ".conv2"}), o);
 }
 
-Act Engine::unet_xformer(Plan& P, const std::string& p, const Act& x, int heads, int text_batch, bool gn_next) {
+Act Engine::unet_xformer(Plan& P, const std::string& p, const Act& x, int heads, int text_batch, bool gn_next, const Act* out) {
   const int C = x.C, B = x.N, N = x.H * x.W, d = C / heads;
   const std::string b = p + ".transformer_blocks.0";
   Act t = group_norm(P, x, norm(p + ".norm"), 1e-6f, false);
@@ -210,7 +211,7 @@ Act Engine::unet_xformer(Plan& P, const std::string& p, const Act& x, int heads,
     Act g = linear(P, n, prep(b + ".ff.net.0.proj", {b + ".ff.net.0.proj"}, true), nullptr, TG_ACT_GEGLU);
     t = linear(P, g, prep(b + ".ff.net.2", {b + ".ff.net.2"}), &t);
   }
-  return linear(P, t, prep(p + ".proj_out", {p + ".proj_out"}), &x, TG_ACT_NONE, gn_next);
+  return linear(P, t, prep(p + ".proj_out", {p + ".proj_out"}), &x, TG_ACT_NONE, gn_next, out);
 }
 
 // every transformer block of the UNet, in execution-independent fixed order (the cross-attention K/V^T cache is keyed by it)
@@ -269,54 +270,98 @@ Act Engine::build_unet(Plan& P, const Act& z, int text_batch, bool text_cached) 
       g_pdl.prev_is_kernel = false;   // a copy node: the next kernel takes a full dependency
     });
   }
+  // torch.cat([h, skip], dim=1) without copies: every skip connection is produced straight into the upper channel slice of
+  // the concat buffer its up-block resnet will read, and the running `h` into the lower slice (I2IT_NO_CATFUSE=1: copy kernels).
+  // Consumer q (pop order, 3 per up block) needs sC(q) channels of `h` in front of the skip.
+  struct SkipSlot { Act cat, skip; int sC; };
+  std::vector<SkipSlot> res;
+  const int rch[4] = {ch[3], ch[2], ch[1], ch[0]};
+  const int total_pushes = 12;                       // conv_in + 4 x 2 block outputs + 3 downsamplers
+  int pushes = 0;
+  const bool fuse = use_catfuse;
+  auto make_slot = [&](int N, int H, int W, int skipC) {
+    const int q = total_pushes - 1 - pushes++, i = q / 3, j = q % 3;
+    SkipSlot t;
+    t.sC = (j == 0) ? (i == 0 ? ch[3] : rch[i - 1]) : rch[i];
+    if (fuse) { t.cat = alloc_act(P, N, H, W, t.sC + skipC); t.skip = t.cat.slice(t.sC, skipC); }
+    return t;
+  };
+  auto push = [&](SkipSlot& t, const Act& produced) { t.skip = produced; res.push_back(t); };   // keeps the producer's GN partials
+  auto h_target = [&]() { return res.back().cat.slice(0, res.back().sC); };                      // where the next `h` goes
+
   Act s;
-  if (has(u + ".conv_in.conv_in_pretrained.weight")) {
+  {
+    SkipSlot t = make_slot(z.N, z.H, z.W, ch[0]);
     ConvOpts oc; oc.gn_out = true;
-    s = conv(P, z, prep_twin(u + ".conv_in.conv_in_pretrained", u + ".conv_in.conv_in_curr", twin_r_), oc);
-  } else {
-    ConvOpts oc; oc.gn_out = true;
-    s = conv(P, z, prep(u + ".conv_in", {u + ".conv_in"}), oc);
+    if (fuse) oc.out = &t.skip;
+    if (has(u + ".conv_in.conv_in_pretrained.weight"))
+      s = conv(P, z, prep_twin(u + ".conv_in.conv_in_pretrained", u + ".conv_in.conv_in_curr", twin_r_), oc);
+    else
+      s = conv(P, z, prep(u + ".conv_in", {u + ".conv_in"}), oc);
+    push(t, s);
   }
-  std::vector<Act> res{s};
   for (int i = 0; i < 4; ++i) {
     const std::string blk = u + ".down_blocks." + std::to_string(i);
     for (int j = 0; j < 2; ++j) {
       // who consumes the output decides whether the producing GEMM takes GroupNorm statistics: the transformer's GroupNorm
       // (i < 3), the next resnet's norm1 (j == 0, or the mid block after the last down block) — not the downsampler conv
-      s = unet_resnet(P, blk + ".resnets." + std::to_string(j), s, true);
-      if (i < 3) s = unet_xformer(P, blk + ".attentions." + std::to_string(j), s, heads[i], text_batch, j == 0);
-      res.push_back(s);
+      SkipSlot t = make_slot(s.N, s.H, s.W, ch[i]);
+      const Act* ov = fuse ? &t.skip : nullptr;
+      s = unet_resnet(P, blk + ".resnets." + std::to_string(j), s, true, i < 3 ? nullptr : ov);
+      if (i < 3) s = unet_xformer(P, blk + ".attentions." + std::to_string(j), s, heads[i], text_batch, j == 0, ov);
+      push(t, s);
     }
     if (i < 3) {
+      SkipSlot t = make_slot(s.N, (s.H + 1) / 2, (s.W + 1) / 2, ch[i]);
       ConvOpts o; o.stride = 2; o.gn_out = true;
+      if (fuse) o.out = &t.skip;
       s = conv(P, s, prep(blk + ".downsamplers.0.conv", {blk + ".downsamplers.0.conv"}), o);
-      res.push_back(s);
+      push(t, s);
     }
   }
+  I2IT_CHECK(pushes == total_pushes, "unet: unexpected number of skip connections");
   s = unet_resnet(P, u + ".mid_block.resnets.0", s, true);
   s = unet_xformer(P, u + ".mid_block.attentions.0", s, heads[3], text_batch, true);
-  s = unet_resnet(P, u + ".mid_block.resnets.1", s, false);          // -> concat (GroupNorm over the concatenation)
+  {
+    Act tgt;
+    if (fuse) tgt = h_target();
+    s = unet_resnet(P, u + ".mid_block.resnets.1", s, false, fuse ? &tgt : nullptr);   // -> concat (GroupNorm over the concatenation)
+  }
   mark(P, "unet_mid", s);
   for (int i = 0; i < 4; ++i) {
     const std::string blk = u + ".up_blocks." + std::to_string(i);
     const int hcount = heads[3 - i];
     for (int j = 0; j < 3; ++j) {
-      Act skip = res.back();
+      SkipSlot t = res.back();
       res.pop_back();
-      Act cat = alloc_act(P, s.N, s.H, s.W, s.C + skip.C);       // torch.cat([h, skip], dim=1)
-      copy_channels(P, s, cat.slice(0, s.C));
-      copy_channels(P, skip, cat.slice(s.C, skip.C));
-      skip = Act();
+      Act cat;
+      if (fuse) {
+        I2IT_CHECK(s.C == t.sC && s.p == t.cat.p && s.H == t.cat.H && s.W == t.cat.W, "unet: concat slot mismatch");
+        cat = t.cat;                                                   // both halves were written in place
+      } else {
+        cat = alloc_act(P, s.N, s.H, s.W, s.C + t.skip.C);             // torch.cat([h, skip], dim=1)
+        copy_channels(P, s, cat.slice(0, s.C));
+        copy_channels(P, t.skip, cat.slice(s.C, t.skip.C));
+      }
+      t = SkipSlot();
       const bool last = (i == 3 && j == 2);                            // the very last block feeds conv_norm_out directly
-      s = unet_resnet(P, blk + ".resnets." + std::to_string(j), cat, i > 0);
-      if (i > 0) s = unet_xformer(P, blk + ".attentions." + std::to_string(j), s, hcount, text_batch, last);
+      // the block's output is the next concat's `h` unless an upsampler (j == 2, i < 3) or conv_norm_out (last) follows
+      Act tgt;
+      const bool to_cat = fuse && j < 2;
+      if (to_cat) tgt = h_target();
+      const Act* ov = to_cat ? &tgt : nullptr;
+      s = unet_resnet(P, blk + ".resnets." + std::to_string(j), cat, i > 0, i > 0 ? nullptr : ov);
+      if (i > 0) s = unet_xformer(P, blk + ".attentions." + std::to_string(j), s, hcount, text_batch, last, ov);
     }
     if (i < 3) {
       // Upsample2D: 2x nearest, or — when the latent is not a multiple of 8 (UNet2DConditionModel.forward: forward_upsample_size)
       // — nearest to the spatial size of the next skip connection (e.g. 14 -> 27 columns for a 560x840 image)
-      const Act& nxt = res.back();
-      s = upsample_to(P, s, nxt.H, nxt.W);
-      s = conv(P, s, prep(blk + ".upsamplers.0.conv", {blk + ".upsamplers.0.conv"}), ConvOpts());
+      const SkipSlot& nxt = res.back();
+      s = upsample_to(P, s, nxt.skip.H, nxt.skip.W);
+      Act tgt;
+      ConvOpts oc;
+      if (fuse) { tgt = h_target(); oc.out = &tgt; }
+      s = conv(P, s, prep(blk + ".upsamplers.0.conv", {blk + ".upsamplers.0.conv"}), oc);
     }
   }
   I2IT_CHECK(res.empty(), "unet: residual stack not consumed");

@@ -2,7 +2,7 @@ set +e
 mkdir -p gpurun_out
 ( time python -m pytest tests -m gpu -q -s 2>&1 ) > gpurun_out/r2d_pytest_full.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/r2d_pytest_full.log
-( I2IT_FLASH_V1=1 I2IT_NO_SPLITK=1 python -m pytest tests/test_gpu_ops.py tests/test_gpu_e2e.py tests/test_gpu_clip.py -m gpu -q 2>&1 ) > gpurun_out/r2d_pytest_v1_nosplitk.log 2>&1
+( I2IT_FLASH_V1=1 I2IT_NO_SPLITK=1 I2IT_NO_CATFUSE=1 python -m pytest tests/test_gpu_ops.py tests/test_gpu_e2e.py tests/test_gpu_clip.py -m gpu -q 2>&1 ) > gpurun_out/r2d_pytest_v1_nosplitk.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/r2d_pytest_v1_nosplitk.log
 B="timeout 600 python bench.py --steps 10 --warmup 3 --configs none --no-cpu-baseline"
 ( time timeout 900 python bench.py --steps 20 --warmup 5 --profile-out gpurun_out/r2d_launch_table.json ) > gpurun_out/r2d_bench.log 2>&1
@@ -11,6 +11,7 @@ B="timeout 600 python bench.py --steps 10 --warmup 3 --configs none --no-cpu-bas
 ( I2IT_NO_GNEPI=1 $B ) > gpurun_out/r2d_bench_nogn.log 2>&1
 ( I2IT_FLASH_V1=1 $B --profile-out gpurun_out/r2d_launch_table_flashv1.json ) > gpurun_out/r2d_bench_flashv1.log 2>&1
 ( I2IT_NO_SPLITK=1 $B ) > gpurun_out/r2d_bench_nosplitk.log 2>&1
+( I2IT_NO_CATFUSE=1 $B ) > gpurun_out/r2d_bench_nocatfuse.log 2>&1
 ( I2IT_NO_HALO=1 $B ) > gpurun_out/r2d_bench_nohalo.log 2>&1
 ( $B --batch 1 ) > gpurun_out/r2d_bench_b1.log 2>&1
 ( I2IT_LIB=$PWD/img2img-turbo_b200/lib/libi2it_trace.so I2IT_TRACE=1 timeout 300 python tests/ncu_target.py 8 512 ) > gpurun_out/r2d_trace_stdout.log 2> gpurun_out/r2d_gemm_timeline_trace.txt
@@ -26,7 +27,7 @@ for n in tg2 tg1 misc; do
   python profiles/line_stalls.py /tmp/ncu/$n.src.csv > gpurun_out/r2d_${n}_line_stalls.txt 2>> gpurun_out/r2d_ncu_sum.log
 done
 tail -3 gpurun_out/r2d_pytest_full.log; tail -3 gpurun_out/r2d_pytest_v1_nosplitk.log
-for f in r2d_bench r2d_bench_again r2d_bench_noidres r2d_bench_nogn r2d_bench_flashv1 r2d_bench_nosplitk r2d_bench_nohalo r2d_bench_b1; do echo "== $f"; python - <<PY
+for f in r2d_bench r2d_bench_again r2d_bench_noidres r2d_bench_nogn r2d_bench_flashv1 r2d_bench_nosplitk r2d_bench_nocatfuse r2d_bench_nohalo r2d_bench_b1; do echo "== $f"; python - <<PY
 import json
 try:
     d=[json.loads(l) for l in open("gpurun_out/$f.log") if l.startswith("{")][-1]

@@ -213,6 +213,36 @@ def test_resolutions_that_are_multiples_of_8_not_64(hw):
     assert m <= 1.5 * m_ref + 2e-3 and mx <= 1.5 * x_ref + 5e-2, (m, m_ref, mx, x_ref)
 
 
+def test_runtime_switches_agree(monkeypatch):
+    """Every A/B switch of the engine selects another hand-written CUDA variant of the same arithmetic: outputs agree, and bit
+    for bit where the variant only changes data movement (in-place concat, TMA vs per-thread stores with the statistics kernel)."""
+    import weights as W
+    cfg, dt = W.TINY, torch.bfloat16
+    sd = W.make_state_dict("pix2pix", cfg, seed=0, perturb_norm=True)
+    x, text, eps, _ = _inputs("pix2pix", 2, 128, cfg)
+    args = (x.to(dt).cuda(), text[:1].to(dt).cuda(), eps.to(dt).cuda())
+
+    def run(**env):
+        for k in ("I2IT_NO_CATFUSE", "I2IT_NO_TMAOUT", "I2IT_NO_GNEPI", "I2IT_NO_SPLITK", "I2IT_FLASH_V1", "I2IT_NO_IDRES",
+                  "I2IT_NO_HALO", "I2IT_NO_PAIR"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        e = _engine("pix2pix", cfg, dt, sd)                       # switches are read when the engine is created
+        e.finalize(1.0, 1.0, 1.0, -1.0)
+        y = e.forward(*args).clone()
+        e.close()
+        return y
+    base = run()
+    assert torch.equal(base, run(I2IT_NO_CATFUSE="1"))
+    assert torch.equal(run(I2IT_NO_GNEPI="1"), run(I2IT_NO_GNEPI="1", I2IT_NO_TMAOUT="1"))
+    for env in ({"I2IT_NO_GNEPI": "1"}, {"I2IT_NO_SPLITK": "1"}, {"I2IT_FLASH_V1": "1"}, {"I2IT_NO_IDRES": "1"},
+                {"I2IT_NO_HALO": "1"}, {"I2IT_NO_PAIR": "1"}):
+        y = run(**env)
+        d = (y.float() - base.float()).abs()
+        assert torch.isfinite(y.float()).all() and d.mean().item() < 4e-3 and d.max().item() < 0.15, (env, d.mean().item(), d.max().item())
+
+
 @pytest.fixture(scope="module")
 def full_model():
     import weights as W
