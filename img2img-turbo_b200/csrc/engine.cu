@@ -746,15 +746,17 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o_in) {
     p.kchunks = ceil_div(x.C, 64);
   } else {
     I2IT_CHECK(o.stride == 2 && k == 3, "conv: only 3x3 stride-2 is on the path");
-    I2IT_CHECK(x.ld == x.C && x.C % 64 == 0 && x.H % 2 == 0 && x.W % 2 == 0, "conv s2: needs dense NHWC, C%64==0, even H/W");
+    I2IT_CHECK(x.ld % 8 == 0 && x.C % 64 == 0 && x.H % 2 == 0 && x.W % 2 == 0, "conv s2: needs NHWC with ld%8==0, C%64==0, even H/W");
     tw = std::min(16, pow2ceil(Wo));
     th = std::min(128 / tw, pow2ceil(Ho));
     tn = 128 / (tw * th);
-    const unsigned long long C = x.C;
-    // 5-D view (px*C + c, xo, py, yo, n) of the dense NHWC input: a stride-2 tap is a plain box in this view
+    const unsigned long long C = x.C, LD = x.ld;
+    // 5-D view (px*ld + c, xo, py, yo, n) of the NHWC input (pixel pitch ld >= C: the input may be a channel slice of a concat
+    // buffer): a stride-2 tap is a plain box in this view.  dim 0 spans the C channels of the even pixel, the gap, and the C
+    // channels of the odd pixel; boxes only ever start at c or ld + c with c + 64 <= C.
     sa.base = x.p;
-    sa.dim[0] = 2 * C; sa.dim[1] = Wo; sa.dim[2] = 2; sa.dim[3] = Ho; sa.dim[4] = x.N;
-    sa.stride[0] = 2 * C * 2; sa.stride[1] = x.W * C * 2; sa.stride[2] = 2ull * x.W * C * 2; sa.stride[3] = 1ull * x.H * x.W * C * 2;
+    sa.dim[0] = LD + C; sa.dim[1] = Wo; sa.dim[2] = 2; sa.dim[3] = Ho; sa.dim[4] = x.N;
+    sa.stride[0] = 2 * LD * 2; sa.stride[1] = x.W * LD * 2; sa.stride[2] = 2ull * x.W * LD * 2; sa.stride[3] = 1ull * x.H * x.W * LD * 2;
     sa.box[0] = 64; sa.box[1] = tw; sa.box[2] = 1; sa.box[3] = th; sa.box[4] = tn;
     p.tdim[0] = ceil_div(Wo, tw); p.tdim[1] = 1; p.tdim[2] = ceil_div(Ho, th); p.tdim[3] = ceil_div(x.N, tn);
     p.box[0] = tw; p.box[1] = 1; p.box[2] = th; p.box[3] = tn;
@@ -767,7 +769,7 @@ Act Engine::conv(Plan& P, const Act& x, const PW& w, const ConvOpts& o_in) {
         const int ex = kx - padl, ey = ky - padl;
         const int px = ex & 1, py = ey & 1;
         const int ox = (ex - px) / 2, oy = (ey - py) / 2;
-        p.tap_a[t][0] = px * x.C; p.tap_a[t][1] = ox; p.tap_a[t][2] = py; p.tap_a[t][3] = oy; p.tap_a[t][4] = 0;
+        p.tap_a[t][0] = px * x.ld; p.tap_a[t][1] = ox; p.tap_a[t][2] = py; p.tap_a[t][3] = oy; p.tap_a[t][4] = 0;
         p.tap_b[t][0] = 0; p.tap_b[t][1] = t; p.tap_b[t][2] = 0; p.tap_b[t][3] = 0;
       }
     p.ostride[0] = ldo; p.ostride[1] = 0; p.ostride[2] = static_cast<long long>(Wo) * ldo;
@@ -956,6 +958,17 @@ Act Engine::linear(Plan& P, const Act& x, const PW& w, const Act* res, int act, 
   return y;
 }
 
+// One ticket counter per image, shared by every GroupNorm launch of a plan: launches are stream-ordered and each one leaves
+// the counters at zero (the block that draws the last ticket re-arms it), so graph replays start clean.
+int* Engine::gn_counters(Plan& P, int images) {
+  I2IT_CHECK(images <= 4096, "group_norm: batch too large for the ticket array");
+  if (!P.gn_counter) {
+    P.gn_counter = static_cast<int*>(P.pool.get_fresh(4096 * sizeof(int)));
+    I2IT_CUDA(cudaMemset(P.gn_counter, 0, 4096 * sizeof(int)));
+  }
+  return P.gn_counter;
+}
+
 Act Engine::group_norm(Plan& P, const Act& x, const NormW& nw, float eps, bool silu) {
   I2IT_CHECK(x.C == nw.C && x.C % 32 == 0 && x.C % 8 == 0, "group_norm: bad channel count " + std::to_string(x.C));
   const int C = x.C, HW = x.H * x.W, cg = C / 32, vecs = C / 8;
@@ -965,17 +978,16 @@ Act Engine::group_norm(Plan& P, const Act& x, const NormW& nw, float eps, bool s
   static const int env_chunks = std::getenv("I2IT_GN_CHUNKS") ? atoi(std::getenv("I2IT_GN_CHUNKS")) : 512;
   const int rows = std::max(1, std::min(1024, env_thr) / vecs), threads = vecs * rows;
   const int chunks = std::max(1, std::min(env_chunks, ceil_div(HW, rows * 4)));
-  // gn_stats on a small tensor (every UNet map): at most 32 chunk partials, summed in gn_apply's prologue -> two launches per
-  // GroupNorm; gn_apply keeps its own (finer) pixel partition
-  const bool small_fallback = static_cast<long long>(HW) * C <= (4ll << 20);
-  const int schunks = small_fallback ? std::min(chunks, 32) : chunks, spix = ceil_div(HW, schunks);
+  // statistics pass over the tensor (no epilogue partials available): at most 64 chunk partials per image
+  const int schunks = std::min(chunks, 64), spix = ceil_div(HW, schunks);
   const int pix = ceil_div(HW, chunks);
   I2IT_CHECK(chunks <= 1024, "group_norm: too many chunks");
-  auto partial = alloc_raw(P, std::max(static_cast<size_t>(x.N) * chunks * 64 * sizeof(float), static_cast<size_t>(x.N) * 4 * 32 * sizeof(double)* 2));
+  auto partial = alloc_raw(P, static_cast<size_t>(x.N) * 64 * 32 * sizeof(double) * 2);   // [N][<=64 chunks][32] double2 (or float2)
   auto stats = alloc_raw(P, static_cast<size_t>(x.N) * 64 * sizeof(float));
   Act y = alloc_act(P, x.N, x.H, x.W, C);
   float* d_part = static_cast<float*>(partial.get());
   float* d_stats = static_cast<float*>(stats.get());
+  int* d_counter = gn_counters(P, x.N);                // zeroed once at build time; every launch leaves it at zero again
   const uint16_t* xp = x.p;
   uint16_t* yp = y.p;
   const long long ximg = x.img(), yimg = y.img();
@@ -983,36 +995,29 @@ Act Engine::group_norm(Plan& P, const Act& x, const NormW& nw, float eps, bool s
   const float* g = nw.g;
   const float* b = nw.b;
   const double inv_count = 1.0 / (static_cast<double>(HW) * cg);
-  const double2* d_part2 = nullptr;
-  const float* partf = nullptr;
-  int nchunk = 0;
   if (x.gn && use_gnepi && x.gn->C == C && x.gn->images == N) {
     // the producer's epilogue already summed the tensor: reduce its per-slot partials (no pass over the tensor itself)
     const GnPart gp = *x.gn;
     const float* pb = gp.buf;
     const int per_row = C / gp.red, epg = cg / gp.red;
     I2IT_CHECK(per_row <= 640, "group_norm: too many partial entries per slot");
-    nchunk = std::max(1, std::min(4, gp.slots_per_image / 64));
+    const int nch = std::max(1, std::min(64, gp.slots_per_image / 16));
     const int e_lanes = std::min(256, pow2ceil(per_row));
-    double2* p2 = reinterpret_cast<double2*>(d_part);          // [N][nchunk][32] double2 fits the (N * chunks * 64 floats) block
-    d_part2 = p2;
-    const int nch = nchunk;
+    double2* p2 = reinterpret_cast<double2*>(d_part);
     add_op(P, [=](cudaStream_t st) {
       launch_k(gn_part_reduce_kernel, dim3(nch, N), dim3(256), 0, st, 0, pb, gp.phases, gp.images, gp.slots_per_image, per_row, epg,
-               e_lanes, p2);
+               e_lanes, p2, d_counter, inv_count, eps, d_stats);
     }, "gn_final_part", 0, 8.0 * gp.phases * N * gp.slots_per_image * per_row);
   } else {
     add_op(P, [=](cudaStream_t st) {
       DISPATCH_T(dt, (launch_k(gn_stats_kernel<T>, dim3(schunks, N), dim3(threads), static_cast<size_t>(rows) * 2 * C * sizeof(float), st, 0,
-                               reinterpret_cast<const T*>(xp), ximg, ldx, C, HW, cg, spix, d_part)));
+                               reinterpret_cast<const T*>(xp), ximg, ldx, C, HW, cg, spix, d_part, d_counter, inv_count, eps, d_stats)));
     }, "gn_stats", 0, 2.0 * N * HW * C);
-    if (small_fallback) { partf = d_part; nchunk = schunks; }
-    else add_op(P, [=](cudaStream_t st) { launch_k(gn_finalize_kernel, dim3(N), dim3(1024), 0, st, 0, d_part, schunks, inv_count, eps, d_stats); }, "gn_final");
   }
   add_op(P, [=](cudaStream_t st) {
     DISPATCH_T(dt, (launch_k(gn_apply_kernel<T>, dim3(chunks, N), dim3(threads), 0, st, 0,
                        reinterpret_cast<const T*>(xp), ximg, ldx, reinterpret_cast<T*>(yp), yimg, ldy, C, HW, cg, pix,
-                       d_stats, g, b, isilu, d_part2, nchunk, inv_count, eps, partf)));
+                       d_stats, g, b, isilu)));
   }, "gn_apply", 0, 4.0 * N * HW * C);
   return y;     // (y carries no statistics: it is a different tensor)
 }

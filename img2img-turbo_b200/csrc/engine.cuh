@@ -121,6 +121,7 @@ struct Plan {
   std::vector<std::shared_ptr<void>> keep;
   std::vector<int> key;                                // (B, H, W, direction, text_batch, text_cached, io_mode)
   void* u8_out_tmp = nullptr;                          // NCHW image the last conv writes when the caller wants uint8 HWC
+  int* gn_counter = nullptr;                           // per-image tickets of the GroupNorm last-block reductions (zero between launches)
   std::vector<std::pair<size_t, const char*>> ranges;  // (first op index, name): NVTX stage ranges of the eager path
   IO io;
   std::vector<std::pair<IO, cudaGraphExec_t>> graphs;  // small cache: one instantiated graph per distinct IO pointer set
@@ -190,6 +191,7 @@ class Engine {
   Act linear(Plan& P, const Act& x, const PW& w, const Act* res = nullptr, int act = TG_ACT_NONE, bool gn_out = false,
              const Act* out = nullptr);
   Act group_norm(Plan& P, const Act& x, const NormW& nw, float eps, bool silu);
+  int* gn_counters(Plan& P, int images);
   Act layer_norm(Plan& P, const Act& x, const NormW& nw, bool to_io_out = false);
   Act upsample2x(Plan& P, const Act& x) { return upsample_to(P, x, 2 * x.H, 2 * x.W); }
   Act upsample_to(Plan& P, const Act& x, int Ho, int Wo);          // F.interpolate(size=(Ho,Wo), mode="nearest")

@@ -9,12 +9,13 @@ namespace i2it {
 // =============================================================================================
 // GroupNorm (+SiLU)   — replaces ATen group_norm + silu at every norm1/norm2/conv_norm_out/
 // Transformer2DModel.norm/attn.group_norm under the reference's vae.encode/unet/vae.decode calls
-// (/root/reference/src/pix2pix_turbo.py:198-203).  Three launches: partial sums (deterministic,
-// no atomics to global), finalize (double), apply.  Algorithmic bytes: 2 reads + 1 write of the tensor.
+// (/root/reference/src/pix2pix_turbo.py:198-203).  Two launches: statistics (from the producing GEMM's epilogue partials, or
+// one pass over the tensor; deterministic; the last block finalises in double) and apply.
 // =============================================================================================
 template <typename T>
 __global__ void gn_stats_kernel(const T* __restrict__ x, long long img_stride, int ld, int C, int HW, int cg,
-                                int pix_per_cta, float* __restrict__ partial /*[N][chunks][32][2]*/) {
+                                int pix_per_cta, float* __restrict__ partial /*[N][chunks][32][2]*/, int* __restrict__ counter,
+                                double inv_count, float eps, float* __restrict__ stats /*[N][32] (mean, rstd)*/) {
   pdl_sync();
   extern __shared__ float s_acc[];   // [rows][2][C]: per-row partials, reduced in a fixed order (bit-reproducible)
   const int vecs = C >> 3;
@@ -56,55 +57,52 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, long long img_stride, i
     }
     float* o = partial + ((static_cast<long long>(n) * gridDim.x + chunk) * 32 + g) * 2;
     o[0] = a; o[1] = b;
+    __threadfence();                                   // the partial is visible before this block's ticket is drawn
   }
-}
-
-static __global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, double inv_count, float eps,
-                                          float* __restrict__ stats /*[N][32][2] = mean, rstd*/) {
-  pdl_sync();
-  // block = 1024 threads = 32 chunk-lanes x 32 groups.  Thread (cl, g) sums chunks cl, cl+32, ... of group g with
-  // independent coalesced float2 loads (a warp reads the 256 B of one chunk row), then the 32 chunk-lanes of a group are
-  // combined in a fixed order through shared memory: reproducible, no atomics, and no dependent-load chain.
-  __shared__ double2 red[32][33];
-  const int n = blockIdx.x, g = threadIdx.x & 31, cl = threadIdx.x >> 5;
-  const float2* base = reinterpret_cast<const float2*>(partial) + static_cast<long long>(n) * chunks * 32 + g;
-  double a = 0.0, b = 0.0;
-  int c = cl;
-  for (; c + 96 < chunks; c += 128) {
-    const float2 v0 = base[static_cast<long long>(c) * 32], v1 = base[static_cast<long long>(c + 32) * 32];
-    const float2 v2 = base[static_cast<long long>(c + 64) * 32], v3 = base[static_cast<long long>(c + 96) * 32];
-    a += static_cast<double>(v0.x); b += static_cast<double>(v0.y);
-    a += static_cast<double>(v1.x); b += static_cast<double>(v1.y);
-    a += static_cast<double>(v2.x); b += static_cast<double>(v2.y);
-    a += static_cast<double>(v3.x); b += static_cast<double>(v3.y);
-  }
-  for (; c < chunks; c += 32) {
-    const float2 v = base[static_cast<long long>(c) * 32];
-    a += static_cast<double>(v.x); b += static_cast<double>(v.y);
-  }
-  red[cl][g] = make_double2(a, b);
+  // Last level in the same launch: the block that draws image n's last ticket sums the chunk partials in ascending chunk
+  // order (so the result does not depend on WHICH block is last: bit-reproducible) and writes (mean, rstd); it re-arms the
+  // counter for the next replay.  The atomic orders the blocks, it never carries data.
+  __shared__ int s_last;
+  __shared__ double2 s_red[32][33];
   __syncthreads();
-  if (cl == 0) {
-    a = 0.0; b = 0.0;
-#pragma unroll 8
-    for (int i = 0; i < 32; ++i) { a += red[i][g].x; b += red[i][g].y; }
+  if (threadIdx.x == 0) s_last = (atomicAdd(&counter[n], 1) == static_cast<int>(gridDim.x) - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int chunks = gridDim.x, g = threadIdx.x & 31, cl = threadIdx.x >> 5, ncl = blockDim.x >> 5;
+  if (cl < ncl) {                                        // whole warps only (blockDim need not be a multiple of 32)
+    const float2* base = reinterpret_cast<const float2*>(partial) + static_cast<long long>(n) * chunks * 32 + g;
+    double a = 0.0, b = 0.0;
+    for (int c = cl; c < chunks; c += ncl) {
+      const float2 v = __ldcg(base + static_cast<long long>(c) * 32);
+      a += static_cast<double>(v.x); b += static_cast<double>(v.y);
+    }
+    s_red[cl][g] = make_double2(a, b);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < ncl; ++i) { a += s_red[i][g].x; b += s_red[i][g].y; }
     const double mean = a * inv_count;
     double var = b * inv_count - mean * mean;
     if (var < 0.0) var = 0.0;
-    stats[(n * 32 + g) * 2] = static_cast<float>(mean);
-    stats[(n * 32 + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    reinterpret_cast<float2*>(stats)[n * 32 + g] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
   }
+  if (threadIdx.x == 0) counter[n] = 0;
 }
 
-// First reduction level over the partials a producing GEMM's epilogue wrote (TapGemmParams::gn_part,
-// [phases][images][slots][per_row] x (sum, sumsq)): block (chunk, n) sums its share of image n's slots with COALESCED loads
-// (threads run along the per_row entries of a slot row), then folds the `epg` entries of each group -> out[n][chunk][32] in
-// double.  The last level (<= 4 chunks) is folded into gn_apply's prologue.  Fixed summation order: reproducible, no atomics.
+// Reduction of the partials a producing GEMM's epilogue wrote (TapGemmParams::gn_part, [phases][images][slots][per_row] x
+// (sum, sumsq)): block (chunk, n) sums its share of image n's slots with COALESCED loads (threads run along the per_row entries
+// of a slot row), folds the `epg` entries of each group -> scratch[n][chunk][32] in double; the block that draws the image's last
+// ticket then sums the chunks in ascending order and writes (mean, rstd).  Up to 64 chunks per image so that the 2 MB of partials
+// of a 512x512x128 image are pulled by 64 CTAs, not 4.  Fixed summation order: reproducible; the atomic only orders blocks.
 static __global__ void gn_part_reduce_kernel(const float* __restrict__ part, int phases, int images, int slots, int per_row,
-                                             int epg, int e_lanes /* pow2, <= 256 */, double2* __restrict__ out) {
+                                             int epg, int e_lanes /* pow2, <= 256 */, double2* __restrict__ scratch,
+                                             int* __restrict__ counter, double inv_count, float eps, float* __restrict__ stats) {
   pdl_sync();
   __shared__ double2 red[256];
   __shared__ double2 ent[640];                      // per_row <= 1280 / 2
+  __shared__ int s_last;
   const int n = blockIdx.y, c = blockIdx.x, nch = gridDim.x, t = threadIdx.x;
   const int s0 = static_cast<int>(static_cast<long long>(c) * slots / nch), s1 = static_cast<int>(static_cast<long long>(c + 1) * slots / nch);
   const int nsl = 256 / e_lanes, te = t % e_lanes, tsl = t / e_lanes;
@@ -141,16 +139,38 @@ static __global__ void gn_part_reduce_kernel(const float* __restrict__ part, int
   if (t < 32) {
     double2 acc = make_double2(0.0, 0.0);
     for (int k = 0; k < epg; ++k) { acc.x += ent[t * epg + k].x; acc.y += ent[t * epg + k].y; }
-    out[(static_cast<long long>(n) * nch + c) * 32 + t] = acc;
+    scratch[(static_cast<long long>(n) * nch + c) * 32 + t] = acc;
+    __threadfence();
   }
+  __syncthreads();
+  if (t == 0) s_last = (atomicAdd(&counter[n], 1) == nch - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last block of image n: thread (k-lane, g) sums chunks k-lane, k-lane + 8, ... ; lanes combined in a fixed order
+  const int g = t & 31, kl = t >> 5;
+  double a = 0.0, b = 0.0;
+  for (int k = kl; k < nch; k += 8) {
+    const double2 v = __ldcg(scratch + (static_cast<long long>(n) * nch + k) * 32 + g);
+    a += v.x; b += v.y;
+  }
+  red[t] = make_double2(a, b);
+  __syncthreads();
+  if (t < 32) {
+    a = 0.0; b = 0.0;
+    for (int i = 0; i < 8; ++i) { a += red[i * 32 + t].x; b += red[i * 32 + t].y; }
+    const double mean = a * inv_count;
+    double var = b * inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    reinterpret_cast<float2*>(stats)[n * 32 + t] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+  }
+  if (t == 0) counter[n] = 0;
 }
 
 template <typename T>
 __global__ void gn_apply_kernel(const T* __restrict__ x, long long ximg, int ldx, T* __restrict__ y, long long yimg,
                                 int ldy, int C, int HW, int cg, int pix_per_cta, const float* __restrict__ stats,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
-                                const double2* __restrict__ part2 = nullptr, int nchunk = 0, double inv_count = 0.0,
-                                float eps = 0.f, const float* __restrict__ partf = nullptr) {
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu) {
   pdl_sync();
   const int vecs = C >> 3;
   const int vx = threadIdx.x % vecs, vy = threadIdx.x / vecs, rows = blockDim.x / vecs;
@@ -162,30 +182,10 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, long long ximg, int ldx
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = vx * 8 + i, g = c / cg;
-    if (g != gprev) {
+    if (g != gprev) {                 // (mean, rstd) were finalised by the statistics launch (last-block reduction)
       gprev = g;
-      if (part2 || partf) {    // last reduction level folded in here: <= 4 double chunk partials (statistics taken in the producing
-                               // GEMM's epilogue) or <= 32 float chunk partials (gn_stats on a small tensor): no finalize launch
-        double a = 0.0, b = 0.0;
-        if (part2) {
-          for (int k = 0; k < nchunk; ++k) {
-            const double2 v = part2[(static_cast<long long>(n) * nchunk + k) * 32 + g];
-            a += v.x; b += v.y;
-          }
-        } else {
-          for (int k = 0; k < nchunk; ++k) {
-            const float2 v = reinterpret_cast<const float2*>(partf)[(static_cast<long long>(n) * nchunk + k) * 32 + g];
-            a += static_cast<double>(v.x); b += static_cast<double>(v.y);
-          }
-        }
-        const double m = a * inv_count;
-        double var = b * inv_count - m * m;
-        if (var < 0.0) var = 0.0;
-        mean = static_cast<float>(m);
-        rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-      } else {
-        mean = stats[(n * 32 + g) * 2]; rstd = stats[(n * 32 + g) * 2 + 1];
-      }
+      const float2 mr = reinterpret_cast<const float2*>(stats)[n * 32 + g];
+      mean = mr.x; rstd = mr.y;
     }
     sc[i] = rstd * gamma[c];
     sh[i] = beta[c] - mean * sc[i];

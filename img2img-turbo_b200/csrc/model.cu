@@ -384,6 +384,12 @@ Plan* Engine::plan_for(int B, int H, int W, int direction, int text_batch, bool 
   std::unique_ptr<Plan> up(new Plan());
   Plan& P = *up;
   P.key = key;
+  // a build that throws must not leave engine members pointing into the dying plan's pool (text_ holds a pool block):
+  // declared after `up`, so it runs before the plan is destroyed
+  struct BuildGuard {
+    Engine* e; bool ok = false;
+    ~BuildGuard() { if (!ok) { e->text_ = Act(); e->text_kv_ = nullptr; } }
+  } guard{this};
   std::vector<Act> skips;
   if (io_mode & IO_U8_OUT) {
     // allocated FIRST and held for the plan's lifetime: pool liveness follows build order, and the last conv writes here
@@ -435,6 +441,7 @@ Plan* Engine::plan_for(int B, int H, int W, int direction, int text_batch, bool 
   I2IT_CUDA(cudaGetLastError());
   Plan* raw_plan = up.get();
   plans_[key] = std::move(up);
+  guard.ok = true;
   return raw_plan;
 }
 

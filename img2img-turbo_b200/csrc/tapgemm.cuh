@@ -54,7 +54,12 @@ constexpr int TG_OSTG_BYTES = TG_EPI_WARPS * TG_OSTG_WARP;
 // 227 KB limit) and the kernels trap with an error word if the runtime base needs more (it is 1 KB aligned in practice).
 constexpr int TG_ALIGN_PAD = 512;
 constexpr int TG_SMEM = TG_STAGES * (TG_A_STAGE + TG_B_STAGE) + TG_BAR_BYTES + TG_BIAS_BYTES + TG_OSTG_BYTES + TG_ALIGN_PAD;
-constexpr int TG_THREADS = (TG_EPI_WARPS + 2) * 32;   // + TMA producer warp + MMA issuer warp
+// + TMA producer warp + MMA issuer warp.  Register reallocation (setmaxnreg) was tried: with two idle warps completing the third
+// warpgroup the epilogue warpgroups can grow to 224 registers while the control warps drop to 64, but ptxas then spills the
+// control roles' hoisted parameter loads (0.5..5 KB of spill traffic depending on the split), so it is compiled out
+// (TG_REGS_EPI = 0); the epilogue fits in the 168 registers a 10-warp CTA gets with ~40 B of spills per round.
+constexpr int TG_REGS_EPI = 0, TG_REGS_CTRL = 64;
+constexpr int TG_THREADS = (TG_EPI_WARPS + (TG_REGS_EPI > 0 ? 4 : 2)) * 32;
 constexpr int TG_ACC_COLS = 256;       // TMEM columns per accumulator stage
 
 enum TgAct : int { TG_ACT_NONE = 0, TG_ACT_CLAMP1 = 1, TG_ACT_GEGLU = 2, TG_ACT_GELU = 3, TG_ACT_QUICKGELU = 4 };   // 3, 4: CLIP MLP
@@ -195,6 +200,9 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// register reallocation between warpgroups (all four warps of a warpgroup execute the same instruction)
+template <int N> __device__ __forceinline__ void reg_inc() { if (N >= 24) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N >= 24 ? N : 24)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), start address
 // advanced by 32 B per UMMA_K=16 step inside the swizzle atom.
@@ -344,7 +352,7 @@ template <typename T>
 __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const CUtensorMap* tmO, const TileCoord& c, int m_tile,
                                               int row, int warp, int j1, int j2, int j3, int j4, int acc, int aphase,
                                               uint32_t tmem_base, float* s_bias, uint32_t ostg_base, uint32_t tfull_bar_addr,
-                                              bool stamp = false) {
+                                              bool stage_bias, bool stamp = false) {
   const int lane = threadIdx.x & 31;
   const uint32_t ostg_warp = ostg_base + warp * TG_OSTG_WARP;   // this warp's store box (1024-byte aligned)
   const int grp = warp >> 2;                     // which of the two warps sharing this TMEM lane quarter
@@ -357,12 +365,16 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const CUte
   const int n0 = c.nt * p.BN;
 
   // stage this tile's bias slice in smem once (a per-chunk global load here stalled the whole epilogue: r01 ncu)
+  // (a launch with a single n-tile stages its one slice into both buffers during the first two tiles and then skips this and the
+  // barrier: 110 tiles per CTA in the 512x512 convs)
   float* sb = s_bias + acc * 256;
-  if (p.bias_mode == TG_BIAS_COL) {
-    for (int cc = warp * 32 + (threadIdx.x & 31); cc < p.BN; cc += TG_EPI_WARPS * 32)
-      sb[cc] = (n0 + cc < p.N) ? p.bias[n0 + cc] : 0.f;
+  if (stage_bias) {
+    if (p.bias_mode == TG_BIAS_COL) {
+      for (int cc = warp * 32 + (threadIdx.x & 31); cc < p.BN; cc += TG_EPI_WARPS * 32)
+        sb[cc] = (n0 + cc < p.N) ? p.bias[n0 + cc] : 0.f;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(TG_EPI_WARPS * 32) : "memory");   // the epilogue warps only
   }
-  asm volatile("bar.sync 1, %0;" ::"n"(TG_EPI_WARPS * 32) : "memory");   // the epilogue warps only
   if (stamp) tg_stamp(p, 7);
   const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + acc * TG_ACC_COLS;
   const bool geglu = p.act == TG_ACT_GEGLU;
@@ -414,13 +426,10 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const CUte
         if (r + TG_EPI_GROUPS < nrounds) load_res(r + TG_EPI_GROUPS);   // next round's residual: in flight during this round's math
       }
       const int nq = geglu ? 4 : 2;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {                          // 32 accumulator columns per step
-        if (q >= nq) break;                                  // warp-uniform
-        uint32_t raw0[16], raw1[16];
-        tc_ld16(taddr + c0 + 32 * q, raw0);
-        tc_ld16(taddr + c0 + 32 * q + 16, raw1);
-        tc_wait_ld();
+      // 32 accumulator columns per step, software-pipelined: the TMEM load of step q+1 is in flight during the math of step q
+      // (tcgen05.wait::ld waits for ALL outstanding loads, so the next load is issued right after the wait)
+      uint32_t xa0[16], xa1[16], xb0[16], xb1[16];       // two 32-column register buffers
+      auto step = [&](int q, const uint32_t (&raw0)[16], const uint32_t (&raw1)[16]) {
         const float* sbq = sb + c0 + 32 * q;
         if (geglu) {
           // interleaved accumulator columns (2j, 2j+1) = (h_j, gate_j) -> output column j = h * gelu(gate): 32 -> 16 columns
@@ -476,10 +485,25 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const CUte
             u0.z = Elem<T>::pack(v[4], v[5]);   u0.w = Elem<T>::pack(v[6], v[7]);
             u1.x = Elem<T>::pack(v[8], v[9]);   u1.y = Elem<T>::pack(v[10], v[11]);
             u1.z = Elem<T>::pack(v[12], v[13]); u1.w = Elem<T>::pack(v[14], v[15]);
+            if (p.gn_part && !row_ok) u0 = u1 = make_uint4(0u, 0u, 0u, 0u);   // clipped by the TMA store; keeps the statistics clean
             sts16(a0, u0);
             sts16(a1, u1);
           }
         }
+      };
+      tc_ld16(taddr + c0, xa0); tc_ld16(taddr + c0 + 16, xa1);
+      tc_wait_ld();
+      tc_ld16(taddr + c0 + 32, xb0); tc_ld16(taddr + c0 + 48, xb1);
+      step(0, xa0, xa1);
+      tc_wait_ld();
+      if (nq > 2) { tc_ld16(taddr + c0 + 64, xa0); tc_ld16(taddr + c0 + 80, xa1); }   // warp-uniform (GEGLU rounds)
+      step(1, xb0, xb1);
+      if (nq > 2) {
+        tc_wait_ld();
+        tc_ld16(taddr + c0 + 96, xb0); tc_ld16(taddr + c0 + 112, xb1);
+        step(2, xa0, xa1);
+        tc_wait_ld();
+        step(3, xb0, xb1);
       }
       fence_async_smem();                                    // generic-proxy writes -> visible to the TMA unit
       __syncwarp();
@@ -490,29 +514,50 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const CUte
       }
       if (p.gn_part) {
         // GroupNorm statistics of the tensor just produced, from the ROUNDED values in the box (what the next layer's GroupNorm
-        // sees): lane l sums columns 2l, 2l+1 over the warp's 32 rows (conflict-free: a row's 32 words sit in 32 banks), then
-        // gn_red/2 neighbouring lanes are combined by shuffles.  One deterministic store per (slot, column group): no atomics.
-        float s = 0.f, qq = 0.f;
-        const unsigned okmask = __ballot_sync(0xffffffffu, row_ok);
-#pragma unroll 8
-        for (int rr = 0; rr < 32; ++rr) {
-          uint32_t w;
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(ostg_warp + rr * 128 + ((((lane >> 2) ^ (rr & 7)) << 4) | ((lane & 3) << 2))));
-          if ((okmask >> rr) & 1u) {
-            const float2 f = Elem<T>::unpack(w);
-            s += f.x + f.y; qq += f.x * f.x + f.y * f.y;
+        // sees; rows outside the tensor were written as zeros).  Lane (rg, ch) = (lane >> 3, lane & 7) reads the 16-byte chunk
+        // ch (8 output columns) of rows rg, rg+4, ..., rg+28: eight independent conflict-free ld.shared.v4 (a quarter warp
+        // covers one 128-byte row), per-column-pair sums in registers, then the four row groups are combined by two shuffle
+        // steps and lanes 0..7 write one (sum, sum of squares) entry per gn_red columns.  Fixed order, no atomics.
+        const int rg = lane >> 3, ch = lane & 7;
+        uint4 w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + rg;
+          w[i] = lds16(ostg_warp + rr * 128 + ((ch ^ (rr & 7)) << 4));
+        }
+        float s2[4] = {0.f, 0.f, 0.f, 0.f}, q2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t ww[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = Elem<T>::unpack(ww[j]);
+            s2[j] += f.x + f.y;
+            q2[j] = fmaf(f.x, f.x, fmaf(f.y, f.y, q2[j]));
           }
         }
-        for (int o = 1; o < (p.gn_red >> 1); o <<= 1) {
-          s += __shfl_xor_sync(0xffffffffu, s, o);
-          qq += __shfl_xor_sync(0xffffffffu, qq, o);
+        const int red = p.gn_red;                            // 2, 4, 8 or 16 columns per entry (warp-uniform)
+        if (red >= 4) { s2[0] += s2[1]; q2[0] += q2[1]; s2[2] += s2[3]; q2[2] += q2[3]; }
+        if (red >= 8) { s2[0] += s2[2]; q2[0] += q2[2]; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if ((red >= 4 && (j & 1)) || (red >= 8 && j)) continue;   // folded above
+          s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8);  q2[j] += __shfl_xor_sync(0xffffffffu, q2[j], 8);
+          s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16); q2[j] += __shfl_xor_sync(0xffffffffu, q2[j], 16);
         }
-        const int lanes_per = p.gn_red >> 1;                 // lanes per output entry (1, 2, 4 or 8)
-        if ((lane & (lanes_per - 1)) == 0 && m_tile < p.gn_mtiles) {   // slots without a valid row still get their zeros
-          const int per_row = (geglu ? (p.N >> 1) : p.N) / p.gn_red;
+        if (red == 16) { s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1); q2[0] += __shfl_xor_sync(0xffffffffu, q2[0], 1); }
+        if (rg == 0 && m_tile < p.gn_mtiles) {               // slots without a valid row still get their zeros
+          const int per_row = p.N / red;
           const long long slot = p.gn_slot0 + static_cast<long long>(m_tile) * 4 + (warp & 3);
-          float2* dst = reinterpret_cast<float2*>(p.gn_part) + slot * per_row + (ocol0 + 2 * lane) / p.gn_red;
-          *dst = make_float2(s, qq);
+          float2* dst = reinterpret_cast<float2*>(p.gn_part) + slot * per_row + (ocol0 + 8 * ch) / red;
+          if (red == 2) {
+            reinterpret_cast<float4*>(dst)[0] = make_float4(s2[0], q2[0], s2[1], q2[1]);
+            reinterpret_cast<float4*>(dst)[1] = make_float4(s2[2], q2[2], s2[3], q2[3]);
+          } else if (red == 4) {
+            *reinterpret_cast<float4*>(dst) = make_float4(s2[0], q2[0], s2[2], q2[2]);
+          } else if (red == 8 || (ch & 1) == 0) {
+            *dst = make_float2(s2[0], q2[0]);
+          }
         }
       }
     }
@@ -619,6 +664,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) tg_stamp(p, 1);
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  if (TG_REGS_EPI > 0) { if (warp >= TG_EPI_WARPS) reg_dec<TG_REGS_CTRL>(); else reg_inc<TG_REGS_EPI>(); }
 
   if (warp == TG_EPI_WARPS) {
     // ================================ TMA producer (whole warp runs the loop, one elected lane issues) ==========
@@ -686,7 +732,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (iter == 0 && lane == 0) tg_stamp(p, 5);                               // first tile fully issued
     }
     if (lane == 0) tg_stamp(p, 6);
-  } else {
+  } else if (warp < TG_EPI_WARPS) {
     // ================================ epilogue (warps 0..7) ================================
     const int row = (warp & 3) * 32 + lane;
     int rr = row;
@@ -699,7 +745,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int acc = iter & 1, aphase = (iter >> 1) & 1;
       const TileCoord c = decode_tile(p, tile);
       epilogue_tile<T>(p, &tmO, c, tile / p.n_tiles, row, warp, j1, j2, j3, j4, acc, aphase, tmem_base, s_bias, ostg,
-                       tfull_bar(acc), iter == 0 && threadIdx.x == 0);
+                       tfull_bar(acc), p.n_tiles > 1 || iter < 2, iter == 0 && threadIdx.x == 0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));

@@ -182,6 +182,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (threadIdx.x == 0) tg_stamp(p, 1);
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  if (TG_REGS_EPI > 0) { if (warp >= TG_EPI_WARPS) reg_dec<TG_REGS_CTRL>(); else reg_inc<TG_REGS_EPI>(); }   // see TG_THREADS
 
   if (warp == TG_EPI_WARPS) {
     // ================================ TMA producer (both CTAs) ================================
@@ -343,7 +344,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       if (lane == 0) tg_stamp(p, 6);
     }
-  } else {
+  } else if (warp < TG_EPI_WARPS) {
     // ================================ epilogue (both CTAs, own 128 rows) ================================
     const int row = (warp & 3) * 32 + lane;
     int rr = row;
@@ -356,7 +357,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int acc = iter & 1, aphase = (iter >> 1) & 1;
       const TileCoord c = decode_pair(pt);
       epilogue_tile<T>(p, &tmO, c, 2 * (pt / p.n_tiles) + static_cast<int>(rank), row, warp, j1, j2, j3, j4, acc, aphase,
-                       tmem_base, s_bias, ostg, tfull_bar(acc), iter == 0 && threadIdx.x == 0);
+                       tmem_base, s_bias, ostg, tfull_bar(acc), p.n_tiles > 1 || iter < 2, iter == 0 && threadIdx.x == 0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
