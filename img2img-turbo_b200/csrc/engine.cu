@@ -112,8 +112,10 @@ Engine::Engine(const i2it_config& c) : cfg(c), dtype(c.dtype) {
   I2IT_CHECK(prop.major == 10, "libi2it is built for sm_100a (B200) only; found compute capability " +
                                    std::to_string(prop.major) + "." + std::to_string(prop.minor));
   num_sms = prop.multiProcessorCount;
-  I2IT_CUDA(cudaFuncSetAttribute(tapgemm_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
-  I2IT_CUDA(cudaFuncSetAttribute(tapgemm_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+  I2IT_CUDA(cudaFuncSetAttribute(tapgemm_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+  I2IT_CUDA(cudaFuncSetAttribute(tapgemm_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+  I2IT_CUDA(cudaFuncSetAttribute(tapgemm_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+  I2IT_CUDA(cudaFuncSetAttribute(tapgemm_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
   I2IT_CUDA(cudaFuncSetAttribute(flash_attn_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
   I2IT_CUDA(cudaFuncSetAttribute(flash_attn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
   I2IT_CUDA(cudaFuncSetAttribute(flash_attn_v1_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
@@ -126,14 +128,18 @@ Engine::Engine(const i2it_config& c) : cfg(c), dtype(c.dtype) {
   trace_on = std::getenv("I2IT_TRACE") != nullptr;
 #endif
   use_tmaout = std::getenv("I2IT_NO_TMAOUT") == nullptr;   // TMA-store epilogue (per-thread stores otherwise)
+  use_ostg2 = std::getenv("I2IT_NO_OSTG2") == nullptr;     // second TMA-store box per epilogue warp where the operand ring can spare 32 KB
+  use_lean = std::getenv("I2IT_NO_LEAN") == nullptr;       // compile-time-stripped epilogue for the plain (no activation) TMA-store launches
   use_gnepi = std::getenv("I2IT_NO_GNEPI") == nullptr;     // GroupNorm statistics in the producing GEMM's epilogue
   use_splitk = std::getenv("I2IT_NO_SPLITK") == nullptr;   // split-K for the 8x8 1280-channel convs
   use_catfuse = std::getenv("I2IT_NO_CATFUSE") == nullptr; // UNet skip concatenations written in place (no copy kernels)
   pair_min_tiles = std::getenv("I2IT_PAIR_MIN_TILES") ? atoll(std::getenv("I2IT_PAIR_MIN_TILES")) : 2ll * num_sms;
   use_idres = std::getenv("I2IT_NO_IDRES") == nullptr;
   use_halo = std::getenv("I2IT_NO_HALO") == nullptr;   // 3x3 convs: one halo tile per k-chunk instead of nine shifted A boxes
-  I2IT_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG2_SMEM));
-  I2IT_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG2_SMEM));
+  I2IT_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG2_SMEM));
+  I2IT_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG2_SMEM));
+  I2IT_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG2_SMEM));
+  I2IT_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG2_SMEM));
   int* h = nullptr;
   I2IT_CUDA(cudaHostAlloc(&h, sizeof(int), cudaHostAllocMapped));
   *h = 0;
@@ -583,11 +589,19 @@ void Engine::launch_gemm(Plan& P, const TmapSpec& sa, TmapSpec sb, const TapGemm
   TmapSpec sb2 = sb2p ? *sb2p : sb;
   if (pair) { sb.box[1] = p.BN / 2; sb2.box[1] = p.BN / 2; p.idesc = make_idesc2(dtype, p.BN); }
   p.halo = (pair && shalo != nullptr && use_halo) ? 1 : 0;
+  p.tma_out = tma_eligible(p, out_from_io) ? 1 : 0;
   {  // smem ring geometry: B stage = the real (half) tile rounded to the 1024-byte swizzle atom, as many stages as fit
     const int brows = pair ? p.BN / 2 : p.BN;
     p.b_stage = (brows * TG_BK * 2 + 1023) / 1024 * 1024;
-    const int budget = pair ? (p.halo ? TG2_DATA_BYTES - TG2_HALO_REGION : TG2_DATA_BYTES) : TG_STAGES * (TG_A_STAGE + TG_B_STAGE);
+    int budget = pair ? (p.halo ? TG2_DATA_BYTES - TG2_HALO_REGION : TG2_DATA_BYTES) : TG_STAGES * (TG_A_STAGE + TG_B_STAGE);
     const int per = (p.halo ? 0 : TG_A_STAGE) + p.b_stage;
+    // a second store box per epilogue warp out of the ring's last 32 KB when at least 4 stages remain and the tile's mainloop
+    // is short (<= 48 k-steps, i.e. <= 96 * BN tensor cycles): those launches wait on TMA-store drain, not on operands; the
+    // long-K launches hide their epilogue anyway and keep the deeper ring
+    int ksteps = 0;
+    for (int t = 0; t < p.num_taps; ++t) ksteps += p.tap_kc[t];
+    p.ostg2 = (use_ostg2 && p.tma_out && ksteps <= 48 && (budget - TG_OSTG_BYTES) / per >= 4) ? 1 : 0;
+    if (p.ostg2) budget -= TG_OSTG_BYTES;
     p.stages = std::max(2, std::min(TG_MAX_STAGES, budget / per));
   }
   const CUtensorMap ta = encode_tmap(sa, dtype), tb = encode_tmap(sb, dtype);
@@ -604,12 +618,11 @@ void Engine::launch_gemm(Plan& P, const TmapSpec& sa, TmapSpec sb, const TapGemm
     grid = static_cast<int>(std::min<long long>(total_tiles, num_sms));
   }
   char shp[160];
-  snprintf(shp, sizeof shp, "M=%.0f N=%d K=%.0f taps=%d BN=%d tiles=%lld grid=%d%s%s%s", m_valid, p.N, k_valid, p.num_taps, p.BN,
-           total_tiles, grid, pair ? (p.halo ? " pair halo" : " pair") : "", tma_eligible(p, out_from_io) ? " tma" : "",
-           (p.gn_part && tma_eligible(p, out_from_io)) ? " gn" : "");
+  snprintf(shp, sizeof shp, "M=%.0f N=%d K=%.0f taps=%d BN=%d tiles=%lld grid=%d st=%d%s%s%s", m_valid, p.N, k_valid, p.num_taps, p.BN,
+           total_tiles, grid, p.stages, pair ? (p.halo ? " pair halo" : " pair") : "", p.tma_out ? (p.ostg2 ? " tma2" : " tma") : "",
+           (p.gn_part && p.tma_out) ? " gn" : "");
   // TMA-store epilogue: the output tensor map has the tile's row dims (extents = logical extents, so ragged edges are clipped
   // by the hardware) and a box of 64 columns x the 32 rows one epilogue warp owns
-  p.tma_out = tma_eligible(p, out_from_io) ? 1 : 0;
   if (!p.tma_out) p.gn_part = nullptr;
   CUtensorMap to = ta;
   if (p.tma_out) {
@@ -635,17 +648,28 @@ void Engine::launch_gemm(Plan& P, const TmapSpec& sa, TmapSpec sb, const TapGemm
     I2IT_CUDA(cudaMemset(p.trace, 0, static_cast<size_t>(grid) * 16 * sizeof(unsigned long long)));
     P.traces.push_back({p.trace, grid, std::string(kind) + " " + shp});
   }
+  {  // division-free tile decode (see fast_div): dividends are tile indices (pair kernel: up to 2 * m-tile index + 1)
+    const long long maxd = std::max<long long>(total_tiles, 2 * m_tiles + 2) + grid;
+    p.magic[0] = make_magic(maxd, p.n_tiles);
+    for (int d = 0; d < 4; ++d) p.magic[d + 1] = make_magic(maxd, p.tdim[d]);
+    for (int d = 0; d < 5; ++d) I2IT_CHECK(p.magic[d] != 0, "tapgemm: tile space too large for the division-free tile decode");
+    p.gn_shift = 0;
+    while ((1 << p.gn_shift) < p.gn_red) ++p.gn_shift;
+  }
+  const bool lean = use_lean && p.tma_out && p.act == TG_ACT_NONE;      // the epilogue variant without activation / direct-store code
   if (pair) {
-    add_op(P, [ta, tb, ta2, tb2, th, to, p, grid, dt, out_from_io, plan](cudaStream_t st) {
+    add_op(P, [ta, tb, ta2, tb2, th, to, p, grid, dt, out_from_io, plan, lean](cudaStream_t st) {
       TapGemmParams q = p;
       if (out_from_io) q.out = plan->io.out;
-      DISPATCH_T(dt, (launch_k(tapgemm2_kernel<T>, dim3(grid), dim3(TG_THREADS), TG2_SMEM, st, 2, ta, tb, ta2, tb2, th, to, q)));
+      if (lean) { DISPATCH_T(dt, (launch_k(tapgemm2_kernel<T, true>, dim3(grid), dim3(TG_THREADS), TG2_SMEM, st, 2, ta, tb, ta2, tb2, th, to, q))); }
+      else { DISPATCH_T(dt, (launch_k(tapgemm2_kernel<T, false>, dim3(grid), dim3(TG_THREADS), TG2_SMEM, st, 2, ta, tb, ta2, tb2, th, to, q))); }
     }, kind, 2.0 * m_valid * p.N * k_valid, bytes, shp);
   } else {
-    add_op(P, [ta, tb, ta2, tb2, to, p, grid, dt, out_from_io, plan](cudaStream_t st) {
+    add_op(P, [ta, tb, ta2, tb2, to, p, grid, dt, out_from_io, plan, lean](cudaStream_t st) {
       TapGemmParams q = p;
       if (out_from_io) q.out = plan->io.out;
-      DISPATCH_T(dt, (launch_k(tapgemm_kernel<T>, dim3(grid), dim3(TG_THREADS), TG_SMEM, st, 0, ta, tb, ta2, tb2, to, q)));
+      if (lean) { DISPATCH_T(dt, (launch_k(tapgemm_kernel<T, true>, dim3(grid), dim3(TG_THREADS), TG_SMEM, st, 0, ta, tb, ta2, tb2, to, q))); }
+      else { DISPATCH_T(dt, (launch_k(tapgemm_kernel<T, false>, dim3(grid), dim3(TG_THREADS), TG_SMEM, st, 0, ta, tb, ta2, tb2, to, q))); }
     }, kind, 2.0 * m_valid * p.N * k_valid, bytes, shp);
   }
 }

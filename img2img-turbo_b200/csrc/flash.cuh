@@ -24,7 +24,7 @@ constexpr int FA_BM = 128, FA_BN = 64, FA_D = 64, FA_STAGES = 3;
 constexpr int FA_Q_BYTES = FA_BM * FA_D * 2;            // 16 KiB
 constexpr int FA_KV_STAGE = 2 * FA_BN * FA_D * 2;       // K 8 KiB + V^T 8 KiB
 constexpr int FA_P_BYTES = FA_BM * FA_BN * 2;           // 16 KiB
-constexpr int FA_SMEM = FA_Q_BYTES + FA_STAGES * FA_KV_STAGE + FA_P_BYTES + 256 + 1024;
+constexpr int FA_SMEM = FA_Q_BYTES + FA_STAGES * FA_KV_STAGE + 2 * FA_P_BYTES + 256 + 1024;   // P is double-buffered
 constexpr int FA_THREADS = 192;
 
 struct FlashParams {
@@ -76,7 +76,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const uint32_t sQ = base;
   const uint32_t sKV = base + FA_Q_BYTES;
   const uint32_t sP = sKV + FA_STAGES * FA_KV_STAGE;
-  const uint32_t bars = sP + FA_P_BYTES;
+  const uint32_t bars = sP + 2 * FA_P_BYTES;
   const uint32_t q_full = bars;
   auto kv_full = [&](int s) { return bars + 8u * (1 + s); };
   auto kv_empty = [&](int s) { return bars + 8u * (1 + FA_STAGES + s); };
@@ -84,8 +84,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const uint32_t s_full0 = bars + 8u * (1 + 2 * FA_STAGES);
   auto s_full = [&](int u) { return s_full0 + 8u * u; };
   auto s_free = [&](int u) { return s_full0 + 16u + 8u * u; };
-  const uint32_t p_full = s_full0 + 32, pv_full = s_full0 + 40;
-  const uint32_t tmem_slot = s_full0 + 48;
+  // P_j goes to smem buffer j&1 and PV_j signals pv_done(j&1): the softmax of step j+1 no longer waits for PV_j (only the
+  // buffer's previous user PV_{j-1}... i.e. step j-2's product, and a rescale of O still waits for everything issued so far)
+  auto p_full = [&](int u) { return s_full0 + 32 + 8u * u; };
+  auto pv_done = [&](int u) { return s_full0 + 48 + 8u * u; };
+  const uint32_t tmem_slot = s_full0 + 64;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x % p.q_tiles;
@@ -98,7 +101,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     mbar_init(q_full, 1);
     for (int s = 0; s < FA_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     for (int u = 0; u < 2; ++u) { mbar_init(s_full(u), 1); mbar_init(s_free(u), 4); }
-    mbar_init(p_full, 4); mbar_init(pv_full, 1);
+    for (int u = 0; u < 2; ++u) { mbar_init(p_full(u), 4); mbar_init(pv_done(u), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmK)) : "memory");
@@ -136,7 +139,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   } else if (warp == 5) {
     // MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma / commit
     mbar_wait(q_full, 0, p.err, 12);
-    const uint64_t qdesc = umma_desc_sw128(sQ), pdesc = umma_desc_sw128(sP);
+    const uint64_t qdesc = umma_desc_sw128(sQ);
     auto issue_qk = [&](int j) {
       const int s = j % FA_STAGES;
       mbar_wait(kv_full(s), (j / FA_STAGES) & 1, p.err, 13);
@@ -157,15 +160,16 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         if (j >= 1) { mbar_wait(s_free((j + 1) & 1), ((j - 1) >> 1) & 1, p.err, 14); tc_fence_after(); }
         issue_qk(j + 1);
       }
-      mbar_wait(p_full, j & 1, p.err, 15);        // P_j is in smem (and PV_{j-1} has been consumed)
+      mbar_wait(p_full(j & 1), (j >> 1) & 1, p.err, 15);   // P_j is in smem buffer j&1 (and any rescale of O is complete)
       tc_fence_after();
       const int s = j % FA_STAGES;
       if (elect_one()) {
         const uint64_t vdesc = umma_desc_sw128(sKV + s * FA_KV_STAGE + FA_BN * FA_D * 2);
+        const uint64_t pdesc = umma_desc_sw128(sP + (j & 1) * FA_P_BYTES);
 #pragma unroll
         for (int k = 0; k < FA_BN / 16; ++k)                 // O accumulates in TMEM across the KV steps
           tc_mma_f16(tPV, pdesc + 2 * k, vdesc + 2 * k, p.idesc, (j > 0 || k > 0) ? 1u : 0u);
-        tc_commit(pv_full);
+        tc_commit(pv_done(j & 1));
         tc_commit(kv_empty(s));                     // K_j and V_j are free once everything issued so far retires
       }
       __syncwarp();
@@ -207,16 +211,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
       }
-      // PV_{j-1} must have landed before O is rescaled and before P_{j-1}'s smem tile is overwritten
-      if (j > 0) {
-        mbar_wait(pv_full, (j - 1) & 1, p.err, 17);
-        tc_fence_after();
-      }
       const bool grow = (fmaxf(m, mx) - m) * sc > TAU;          // first tile: m = -inf -> true
       if (j == 0) {
         m = mx;
       } else if (__any_sync(0xffffffffu, grow)) {
-        // some row of this warp outgrew its reference maximum: rescale the warp's 32 O rows in TMEM (factor 1 for the others)
+        // some row of this warp outgrew its reference maximum: rescale the warp's 32 O rows in TMEM (factor 1 for the others).
+        // Every PV issued so far must have landed first: PV_{j-1} is the last one (MMAs retire in order).
+        mbar_wait(pv_done((j - 1) & 1), ((j - 1) >> 1) & 1, p.err, 17);
+        tc_fence_after();
         const float m_new = grow ? fmaxf(m, mx) : m;
         const float factor = fast_exp2((m - m_new) * sc);
         uint32_t o[32];
@@ -232,6 +234,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         l *= factor;
         m = m_new;
       }
+      // P buffer j&1 was last read by PV_{j-2}
+      if (j >= 2) mbar_wait(pv_done(j & 1), ((j - 2) >> 1) & 1, p.err, 19);
+      const uint32_t sPj = sP + (j & 1) * FA_P_BYTES;
       const float neg_ms = -m * sc;
       // p = exp2(s*scale - m*scale) (one FFMA + one MUFU per element), fp32 row sum of the unrounded p, pack to 16 bit, write the
       // swizzled K-major P tile
@@ -260,7 +265,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
         for (int g = 0; g < 4; ++g) {               // 16-byte group g' = half*4+g holds keys 8g'..8g'+7 of this row
           const int gg = half * 4 + g;
-          sts16(sP + row * 128 + ((gg ^ (row & 7)) << 4), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          sts16(sPj + row * 128 + ((gg ^ (row & 7)) << 4), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
         }
       }
       l += psum;
@@ -268,10 +273,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc_fence_before();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(p_full(j & 1));
     }
     // last PV, then the only read of O
-    mbar_wait(pv_full, (nkv - 1) & 1, p.err, 18);
+    mbar_wait(pv_done((nkv - 1) & 1), ((nkv - 1) >> 1) & 1, p.err, 18);
     tc_fence_after();
     const int q = qt * FA_BM + row;
     const float inv = 1.0f / l;

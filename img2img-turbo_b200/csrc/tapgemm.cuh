@@ -97,6 +97,9 @@ struct TapGemmParams {
   int act;
   int* err;               // device error word (watchdog)
   int tma_out;            // 1: 64-column rounds are staged in smem and stored by TMA (I2IT_NO_TMAOUT=1 -> 0: per-thread stores)
+  int ostg2;              // 1: every epilogue warp alternates between TWO store boxes (the second set lives in the last 32 KB of the
+                          // operand ring, which the host then sizes 32 KB smaller): a round no longer waits for the TMA store of
+                          // the previous round to drain its box (I2IT_NO_OSTG2=1 -> 0)
   // GroupNorm statistics of the OUTPUT tensor, taken from the staged (rounded) tile: per 32-row slot and per `gn_red` columns,
   // (sum, sum of squares) -> gn_part[(slot0 + m_tile*4 + quarter) * (N/gn_red) + col/gn_red][2]; nullptr = off
   float* gn_part;
@@ -105,6 +108,10 @@ struct TapGemmParams {
   int ksplit, kc_per;
   long long split_ostride;
   int gn_red, gn_slot0, gn_mtiles;   // gn_mtiles: m-tiles of the launch (the pair kernel's odd tail tile has no slot)
+  int gn_shift;                      // log2(gn_red)
+  // tile decode without integer division: magic[i] = floor(2^32 / d_i) + 1 for d = (n_tiles, tdim[0..3]); exact while
+  // tile * d < 2^32 (the host refuses larger tile spaces)
+  uint32_t magic[5];
   unsigned long long* trace;   // optional (I2IT_TRACE=1): 16 %clock64 stamps per CTA at the phase boundaries, else nullptr
 };
 
@@ -167,6 +174,7 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* tm, uint32_t src
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // one lane of a fully converged warp (warp-uniform control flow keeps descriptors/addresses in uniform registers)
@@ -240,16 +248,27 @@ __device__ __forceinline__ void tg_stamp(const TapGemmParams& p, int slot) {
 struct TileCoord {
   int nt, t[4], split;
 };
+// x / d with the host's magic number (one IMAD.HI instead of ~20 instructions; the tile loops of all three roles decode a tile
+// per iteration and the r02g profile charged 137 of the epilogue's 1460 instructions per tile to these divisions)
+__device__ __forceinline__ int fast_div(int x, int d, uint32_t magic) {
+  const int q = static_cast<int>(__umulhi(static_cast<uint32_t>(x), magic));      // branch-free: one IMAD.HI + one select
+  return d == 1 ? x : q;
+}
 __device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int tile) {
   TileCoord c;
-  c.nt = tile % p.n_tiles;
-  int r = tile / p.n_tiles;
-  c.t[0] = r % p.tdim[0]; r /= p.tdim[0];
-  c.t[1] = r % p.tdim[1]; r /= p.tdim[1];
-  c.t[2] = r % p.tdim[2]; r /= p.tdim[2];
-  c.t[3] = r % p.tdim[3];
-  c.split = r / p.tdim[3];                       // 0 unless ksplit > 1 (slowest index)
+  int r = fast_div(tile, p.n_tiles, p.magic[0]), q;
+  c.nt = tile - r * p.n_tiles;
+  q = fast_div(r, p.tdim[0], p.magic[1]); c.t[0] = r - q * p.tdim[0]; r = q;
+  q = fast_div(r, p.tdim[1], p.magic[2]); c.t[1] = r - q * p.tdim[1]; r = q;
+  q = fast_div(r, p.tdim[2], p.magic[3]); c.t[2] = r - q * p.tdim[2]; r = q;
+  q = fast_div(r, p.tdim[3], p.magic[4]); c.t[3] = r - q * p.tdim[3];
+  c.split = q;                                   // 0 unless ksplit > 1 (slowest index)
   return c;
+}
+inline uint32_t make_magic(long long max_dividend, int d) {   // host; 0 = the tile space is too large for the 32-bit magic (caller raises)
+  if (d <= 1) return 1u;                                        // unused (fast_div selects x for d == 1)
+  if (max_dividend * d >= (1ll << 32)) return 0u;
+  return static_cast<uint32_t>((1ull << 32) / static_cast<unsigned>(d)) + 1u;
 }
 
 // One 16-column chunk of one accumulator row: alpha, bias, (GEGLU), residual, clamp, single rounding, store.
@@ -348,41 +367,41 @@ __device__ __forceinline__ void epilogue_chunk(const TapGemmParams& p, const uin
 //     the residual is fetched with coalesced loads before the accumulator wait and added from the box; optional GroupNorm
 //     statistics of the rounded output come from the box as well;
 //   * direct: each thread stores its own row (fp32 logits, NCHW image, row-bias V^T, channel counts that are not multiples of 64).
-template <typename T>
+// LEAN (compile time): the launch takes the TMA-store path with no activation (every conv / linear of the path except the GEGLU,
+// GELU and clamp epilogues) -> the activation branches, the GEGLU rounds and the whole direct path are not compiled in; half the
+// code, fewer instruction-cache misses (17 % of the r02g stall samples were no_inst).
+template <typename T, bool LEAN>
 __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const CUtensorMap* tmO, const TileCoord& c, int m_tile,
                                               int row, int warp, int j1, int j2, int j3, int j4, int acc, int aphase,
-                                              uint32_t tmem_base, float* s_bias, uint32_t ostg_base, uint32_t tfull_bar_addr,
-                                              bool stage_bias, bool stamp = false) {
+                                              uint32_t tmem_base, float* s_bias, uint32_t ostg_base, uint32_t ostg2_base,
+                                              int& box_sel, uint32_t tfull_bar_addr, bool stage_bias, bool stamp = false) {
   const int lane = threadIdx.x & 31;
-  const uint32_t ostg_warp = ostg_base + warp * TG_OSTG_WARP;   // this warp's store box (1024-byte aligned)
+  // this warp's store box(es), 1024-byte aligned; with two boxes the warp alternates per round (box_sel persists across tiles)
+  const uint32_t ostg_w0 = ostg_base + warp * TG_OSTG_WARP, ostg_w1 = p.ostg2 ? ostg2_base + warp * TG_OSTG_WARP : ostg_w0;
   const int grp = warp >> 2;                     // which of the two warps sharing this TMEM lane quarter
   const int g1 = c.t[0] * p.box[0] + j1, g2 = c.t[1] * p.box[1] + j2, g3 = c.t[2] * p.box[2] + j3,
             g4 = c.t[3] * p.box[3] + j4;
   const bool row_ok = (g1 < p.ext[0]) && (g2 < p.ext[1]) && (g3 < p.ext[2]) && (g4 < p.ext[3]);
-  const long long obase = g1 * p.ostride[0] + g2 * p.ostride[1] + g3 * p.ostride[2] + g4 * p.ostride[3] + c.split * p.split_ostride;
-  const long long rbase = g1 * p.rstride[0] + g2 * p.rstride[1] + g3 * p.rstride[2] + g4 * p.rstride[3];
-  const float rbias = (p.bias_mode == TG_BIAS_ROW && row_ok) ? p.bias[g1] : 0.0f;
+  const long long rbase = p.res ? g1 * p.rstride[0] + g2 * p.rstride[1] + g3 * p.rstride[2] + g4 * p.rstride[3] : 0;
   const int n0 = c.nt * p.BN;
 
   // stage this tile's bias slice in smem once (a per-chunk global load here stalled the whole epilogue: r01 ncu)
   // (a launch with a single n-tile stages its one slice into both buffers during the first two tiles and then skips this and the
   // barrier: 110 tiles per CTA in the 512x512 convs)
   float* sb = s_bias + acc * 256;
-  if (stage_bias) {
-    if (p.bias_mode == TG_BIAS_COL) {
-      for (int cc = warp * 32 + (threadIdx.x & 31); cc < p.BN; cc += TG_EPI_WARPS * 32)
-        sb[cc] = (n0 + cc < p.N) ? p.bias[n0 + cc] : 0.f;
-    }
+  if (stage_bias) {      // no column bias: zeros, so the rounds add unconditionally (one FFMA: alpha * acc + bias)
+    for (int cc = warp * 32 + (threadIdx.x & 31); cc < p.BN; cc += TG_EPI_WARPS * 32)
+      sb[cc] = (p.bias_mode == TG_BIAS_COL && n0 + cc < p.N) ? p.bias[n0 + cc] : 0.f;
     asm volatile("bar.sync 1, %0;" ::"n"(TG_EPI_WARPS * 32) : "memory");   // the epilogue warps only
   }
   if (stamp) tg_stamp(p, 7);
   const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + acc * TG_ACC_COLS;
-  const bool geglu = p.act == TG_ACT_GEGLU;
+  const bool geglu = !LEAN && p.act == TG_ACT_GEGLU;
 
-  if (p.tma_out) {
+  if (LEAN || p.tma_out) {
     // ================= TMA-store path: rounds of 64 OUTPUT columns (64 accumulator columns, 128 for GEGLU) =================
     const int acols = geglu ? 128 : 64;                       // accumulator columns per round
-    const int nrounds = p.BN / acols;                         // host guarantees BN % acols == 0 and N % acols == 0
+    const int nrounds = p.BN >> (geglu ? 7 : 6);              // host guarantees BN % acols == 0 and N % acols == 0
     const bool res_on = p.res != nullptr && !geglu;
     // Residual prefetch: independent of the accumulator, so it is requested BEFORE the accumulator wait and its latency
     // overlaps the mainloop.  Instruction i loads rows 4i..4i+3 of the warp's 32 (8 lanes x 16 B = one full 128-byte row
@@ -405,7 +424,6 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const CUte
     mbar_wait(tfull_bar_addr, aphase, p.err, 4);
     tc_fence_after();
     if (stamp) tg_stamp(p, 8);
-    const uint32_t my_row = ostg_warp + lane * 128;
     const int sw = lane & 7;
 #pragma unroll
     for (int k = 0; k < TG_EPI_RPW / 2; ++k) {
@@ -413,9 +431,12 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const CUte
       if (r >= nrounds) break;                               // warp-uniform
       const int c0 = acols * r;                              // accumulator column of this round inside the tile
       if (n0 + c0 >= p.N) break;                             // whole round beyond N (last n-tile): nothing to store
-      // the previous TMA store out of this box must have finished READING it
-      if (lane == 0) bulk_wait_read0();
+      // the previous TMA store out of this box must have finished READING it (two boxes: the store before the previous one)
+      const uint32_t ostg_warp = box_sel ? ostg_w1 : ostg_w0;
+      const uint32_t my_row = ostg_warp + lane * 128;
+      if (lane == 0) { if (p.ostg2) bulk_wait_read1(); else bulk_wait_read0(); }
       __syncwarp();
+      box_sel ^= p.ostg2;
       if (res_on) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -430,6 +451,7 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const CUte
       // (tcgen05.wait::ld waits for ALL outstanding loads, so the next load is issued right after the wait)
       uint32_t xa0[16], xa1[16], xb0[16], xb1[16];       // two 32-column register buffers
       auto step = [&](int q, const uint32_t (&raw0)[16], const uint32_t (&raw1)[16]) {
+        const uint32_t sbq_s = smem_u32(sb + c0 + 32 * q);      // 16-byte aligned: the bias slice comes in as ld.shared.v4
         const float* sbq = sb + c0 + 32 * q;
         if (geglu) {
           // interleaved accumulator columns (2j, 2j+1) = (h_j, gate_j) -> output column j = h * gelu(gate): 32 -> 16 columns
@@ -454,17 +476,21 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const CUte
             const uint32_t* raw = h ? raw1 : raw0;
             float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
-            if (p.bias_mode == TG_BIAS_COL) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += sbq[16 * h + i];
+            for (int i4 = 0; i4 < 4; ++i4) {               // v = alpha * acc + bias (zeros staged when there is no column bias)
+              const uint4 bq = lds16(sbq_s + (16 * h + 4 * i4) * 4);
+              v[4 * i4] = fmaf(__uint_as_float(raw[4 * i4]), p.alpha, __uint_as_float(bq.x));
+              v[4 * i4 + 1] = fmaf(__uint_as_float(raw[4 * i4 + 1]), p.alpha, __uint_as_float(bq.y));
+              v[4 * i4 + 2] = fmaf(__uint_as_float(raw[4 * i4 + 2]), p.alpha, __uint_as_float(bq.z));
+              v[4 * i4 + 3] = fmaf(__uint_as_float(raw[4 * i4 + 3]), p.alpha, __uint_as_float(bq.w));
             }
-            if (p.act == TG_ACT_GELU) {
+            if (!LEAN) {
+              if (p.act == TG_ACT_GELU) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = gelu_erf_f(v[i]);
-            } else if (p.act == TG_ACT_QUICKGELU) {
+                for (int i = 0; i < 16; ++i) v[i] = gelu_erf_f(v[i]);
+              } else if (p.act == TG_ACT_QUICKGELU) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = quick_gelu_f(v[i]);
+                for (int i = 0; i < 16; ++i) v[i] = quick_gelu_f(v[i]);
+              }
             }
             const uint32_t a0 = my_row + (((4 * q + 2 * h) ^ sw) << 4), a1 = my_row + (((4 * q + 2 * h + 1) ^ sw) << 4);
             if (res_on) {
@@ -476,7 +502,7 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const CUte
                 v[2 * i] += f.x; v[2 * i + 1] += f.y;
               }
             }
-            if (p.act == TG_ACT_CLAMP1) {
+            if (!LEAN && p.act == TG_ACT_CLAMP1) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = fminf(fmaxf(v[i], -1.0f), 1.0f);
             }
@@ -496,9 +522,9 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const CUte
       tc_ld16(taddr + c0 + 32, xb0); tc_ld16(taddr + c0 + 48, xb1);
       step(0, xa0, xa1);
       tc_wait_ld();
-      if (nq > 2) { tc_ld16(taddr + c0 + 64, xa0); tc_ld16(taddr + c0 + 80, xa1); }   // warp-uniform (GEGLU rounds)
+      if (!LEAN && nq > 2) { tc_ld16(taddr + c0 + 64, xa0); tc_ld16(taddr + c0 + 80, xa1); }   // warp-uniform (GEGLU rounds)
       step(1, xb0, xb1);
-      if (nq > 2) {
+      if (!LEAN && nq > 2) {
         tc_wait_ld();
         tc_ld16(taddr + c0 + 96, xb0); tc_ld16(taddr + c0 + 112, xb1);
         step(2, xa0, xa1);
@@ -547,9 +573,9 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const CUte
         }
         if (red == 16) { s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1); q2[0] += __shfl_xor_sync(0xffffffffu, q2[0], 1); }
         if (rg == 0 && m_tile < p.gn_mtiles) {               // slots without a valid row still get their zeros
-          const int per_row = p.N / red;
+          const int per_row = p.N >> p.gn_shift;
           const long long slot = p.gn_slot0 + static_cast<long long>(m_tile) * 4 + (warp & 3);
-          float2* dst = reinterpret_cast<float2*>(p.gn_part) + slot * per_row + (ocol0 + 8 * ch) / red;
+          float2* dst = reinterpret_cast<float2*>(p.gn_part) + slot * per_row + ((ocol0 + 8 * ch) >> p.gn_shift);
           if (red == 2) {
             reinterpret_cast<float4*>(dst)[0] = make_float4(s2[0], q2[0], s2[1], q2[1]);
             reinterpret_cast<float4*>(dst)[1] = make_float4(s2[2], q2[2], s2[3], q2[3]);
@@ -564,7 +590,10 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const CUte
     return;
   }
 
+  if constexpr (LEAN) return;
   // ================= direct path =================
+  const long long obase = g1 * p.ostride[0] + g2 * p.ostride[1] + g3 * p.ostride[2] + g4 * p.ostride[3] + c.split * p.split_ostride;
+  const float rbias = (p.bias_mode == TG_BIAS_ROW && row_ok) ? p.bias[g1] : 0.0f;
   // Residual reads do not depend on the accumulator: this thread's WHOLE residual slice (its row x the 32-column rounds
   // r = grp, grp+2, ...; <= 256 B) is requested before the accumulator wait, so global-load latency overlaps the mainloop.
   const int nrounds = (p.BN + 31) >> 5;
@@ -611,7 +640,7 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& p, const CUte
   }
 }
 
-template <typename T>
+template <typename T, bool LEAN>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
@@ -627,6 +656,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t sA = base;
   const uint32_t sB = base + NS * TG_A_STAGE;
   const uint32_t ostg = base + TG_STAGES * (TG_A_STAGE + TG_B_STAGE);   // epilogue store boxes (1024-byte aligned)
+  const uint32_t ostg2 = ostg - TG_OSTG_BYTES;                          // optional second set: the ring's last 32 KB (p.ostg2)
   const uint32_t bars = ostg + TG_OSTG_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (TG_MAX_STAGES + s); };
@@ -667,7 +697,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (TG_REGS_EPI > 0) { if (warp >= TG_EPI_WARPS) reg_dec<TG_REGS_CTRL>(); else reg_inc<TG_REGS_EPI>(); }
 
   if (warp == TG_EPI_WARPS) {
-    // ================================ TMA producer (whole warp runs the loop, one elected lane issues) ==========
+    // ================================ TMA producer: ONE elected thread runs the whole loop ==========
+    if (elect_one()) {
     int stage = 0, phase = 0;
     const uint32_t tx_bytes = TG_A_STAGE + static_cast<uint32_t>(p.BN) * (TG_BK * 2);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -680,14 +711,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const CUtensorMap* ta = p.tap_src[t] ? &tmA2 : &tmA;
         const CUtensorMap* tb = p.tap_src[t] ? &tmB2 : &tmB;
         mbar_wait(empty_bar(stage), phase ^ 1, p.err, 1);
-        if (elect_one()) {
+        {
           mbar_expect_tx(full_bar(stage), tx_bytes);
           tma_load_5d(sA + stage * TG_A_STAGE, ta, full_bar(stage), kc * TG_BK + p.tap_a[t][0],
                       a1 + p.tap_a[t][1], a2 + p.tap_a[t][2], a3 + p.tap_a[t][3], a4 + p.tap_a[t][4]);
           tma_load_5d(sB + stage * BST, tb, full_bar(stage), kc * TG_BK + p.tap_b[t][0], n0,
                       b2 + p.tap_b[t][1], b3 + p.tap_b[t][2], b4 + p.tap_b[t][3]);
         }
-        __syncwarp();
         if (++stage == NS) { stage = 0; phase ^= 1; }
       };
       const int kc0 = nsplit > 1 ? c.split * p.kc_per : 0, kc1 = nsplit > 1 ? min(p.kchunks, kc0 + p.kc_per) : p.kchunks;
@@ -696,11 +726,15 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (c.split == 0)
         for (int t = p.nprim; t < p.num_taps; ++t)
           for (int kc = 0; kc < p.tap_kc[t]; ++kc) load_step(t, kc);
-      if (tile == static_cast<int>(blockIdx.x) && lane == 0) tg_stamp(p, 2);   // first tile's loads all issued
+      if (tile == static_cast<int>(blockIdx.x)) tg_stamp(p, 2);   // first tile's loads all issued
     }
-    if (lane == 0) tg_stamp(p, 3);
+    tg_stamp(p, 3);
+    }
+    __syncwarp();
   } else if (warp == TG_EPI_WARPS + 1) {
-    // ================================ MMA issuer (warp-uniform loop, elected lane issues) ================================
+    // ================================ MMA issuer: ONE elected thread runs the whole loop ================================
+    // (no per-step elect / reconvergence: for the short MMAs, BN <= 128, the issue loop itself is the critical path — r02h)
+    if (elect_one()) {
     int stage = 0, phase = 0, iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       const int acc = iter & 1, aphase = (iter >> 1) & 1;
@@ -716,8 +750,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int s = 0; s < tsteps; ++s) {
         mbar_wait(full_bar(stage), phase, p.err, 3);
         tc_fence_after();
-        if (iter == 0 && s == 0 && lane == 0) tg_stamp(p, 4);                   // first operands landed
-        if (elect_one()) {
+        if (iter == 0 && s == 0) tg_stamp(p, 4);                                // first operands landed
+        {
           const uint64_t adesc = umma_desc_sw128(sA + stage * TG_A_STAGE);
           const uint64_t bdesc = umma_desc_sw128(sB + stage * BST);
 #pragma unroll
@@ -726,12 +760,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_commit(empty_bar(stage));               // frees the smem slot when these MMAs retire
           if (s == tsteps - 1) tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
         }
-        __syncwarp();
         if (++stage == NS) { stage = 0; phase ^= 1; }
       }
-      if (iter == 0 && lane == 0) tg_stamp(p, 5);                               // first tile fully issued
+      if (iter == 0) tg_stamp(p, 5);                                            // first tile fully issued
     }
-    if (lane == 0) tg_stamp(p, 6);
+    tg_stamp(p, 6);
+    }
+    __syncwarp();
   } else if (warp < TG_EPI_WARPS) {
     // ================================ epilogue (warps 0..7) ================================
     const int row = (warp & 3) * 32 + lane;
@@ -740,12 +775,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int j2 = rr % p.box[1]; rr /= p.box[1];
     const int j3 = rr % p.box[2];
     const int j4 = rr / p.box[2];
-    int iter = 0;
+    int iter = 0, box_sel = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       const int acc = iter & 1, aphase = (iter >> 1) & 1;
       const TileCoord c = decode_tile(p, tile);
-      epilogue_tile<T>(p, &tmO, c, tile / p.n_tiles, row, warp, j1, j2, j3, j4, acc, aphase, tmem_base, s_bias, ostg,
-                       tfull_bar(acc), p.n_tiles > 1 || iter < 2, iter == 0 && threadIdx.x == 0);
+      epilogue_tile<T, LEAN>(p, &tmO, c, fast_div(tile, p.n_tiles, p.magic[0]), row, warp, j1, j2, j3, j4, acc, aphase, tmem_base, s_bias, ostg, ostg2,
+                       box_sel, tfull_bar(acc), p.n_tiles > 1 || iter < 2, iter == 0 && threadIdx.x == 0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));

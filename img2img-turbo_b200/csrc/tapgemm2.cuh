@@ -98,7 +98,7 @@ inline uint32_t make_idesc2(int dtype, int bn) {
 }
 
 // tmB / tmB2 here are encoded with a box of BN/2 rows.  gridDim.x must be even (cluster dims (2,1,1)).
-template <typename T>
+template <typename T, bool LEAN>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
@@ -116,6 +116,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t sA = base;
   const uint32_t sB = base + (p.halo ? TG2_HALO_REGION : NS * TG_A_STAGE);
   const uint32_t ostg = base + TG2_DATA_BYTES;                // epilogue store boxes (1024-byte aligned)
+  const uint32_t ostg2 = ostg - TG_OSTG_BYTES;                // optional second set: the ring's last 32 KB (p.ostg2)
   const uint32_t bars = ostg + TG_OSTG_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (TG_MAX_STAGES + s); };
@@ -145,12 +146,13 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   // pair tile -> this CTA's (n tile, m tile) coordinates
   auto decode_pair = [&](int pt) {
     TileCoord c;
-    c.nt = pt % p.n_tiles;
-    int r = 2 * (pt / p.n_tiles) + static_cast<int>(rank);
-    c.t[0] = r % p.tdim[0]; r /= p.tdim[0];
-    c.t[1] = r % p.tdim[1]; r /= p.tdim[1];
-    c.t[2] = r % p.tdim[2]; r /= p.tdim[2];
-    c.t[3] = r;                               // may exceed tdim[3] for the odd tail: rows then fail the extent check
+    const int mp = fast_div(pt, p.n_tiles, p.magic[0]);
+    c.nt = pt - mp * p.n_tiles;
+    int r = 2 * mp + static_cast<int>(rank), q;
+    q = fast_div(r, p.tdim[0], p.magic[1]); c.t[0] = r - q * p.tdim[0]; r = q;
+    q = fast_div(r, p.tdim[1], p.magic[2]); c.t[1] = r - q * p.tdim[1]; r = q;
+    q = fast_div(r, p.tdim[2], p.magic[3]); c.t[2] = r - q * p.tdim[2];
+    c.t[3] = q;                               // may exceed tdim[3] for the odd tail: rows then fail the extent check
     c.split = 0;                              // split-K is a 1-CTA-kernel feature
     return c;
   };
@@ -185,7 +187,10 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (TG_REGS_EPI > 0) { if (warp >= TG_EPI_WARPS) reg_dec<TG_REGS_CTRL>(); else reg_inc<TG_REGS_EPI>(); }   // see TG_THREADS
 
   if (warp == TG_EPI_WARPS) {
-    // ================================ TMA producer (both CTAs) ================================
+    // ================================ TMA producer (both CTAs): ONE elected thread runs the whole loop =====================
+    // (after the MMA issue loop was trimmed the r02i profile showed the MMA thread waiting for operands on 91 % of the steps of
+    // the N = 128 halo convs: this loop — per-step elect, parameter-table lookups — had become the critical path)
+    if (elect_one()) {
     int stage = 0, phase = 0, hs = 0, hphase = 0;
 #ifdef I2IT_HALO_X2
     int s2 = 0, a2phase = 0;
@@ -201,7 +206,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const CUtensorMap* ta = p.tap_src[t] ? &tmA2 : &tmA;
         const CUtensorMap* tb = p.tap_src[t] ? &tmB2 : &tmB;
         mbar_wait(empty_bar(stage), phase ^ 1, p.err, 21);
-        if (elect_one()) {
+        {
           if (leader) mbar_expect_tx(full_bar(stage), tx_bytes);
           else mbar_arrive_cluster(full_bar(stage), 0);
           tma_load_5d_2sm(sA + stage * TG_A_STAGE, ta, full_bar(stage), kc * TG_BK + p.tap_a[t][0], a1 + p.tap_a[t][1],
@@ -209,29 +214,24 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tma_load_5d_2sm(sB + stage * BST, tb, full_bar(stage), kc * TG_BK + p.tap_b[t][0], n0,
                           b2 + p.tap_b[t][1], b3 + p.tap_b[t][2], b4 + p.tap_b[t][3]);
         }
-        __syncwarp();
         if (++stage == NS) { stage = 0; phase ^= 1; }
       };
       if (p.halo) {
         for (int kc = 0; kc < p.kchunks; ++kc) {
           // one halo tile (rows y0-1 .. y0+16, pixels x0-1 .. x0+14) serves all nine taps of this k-chunk
           mbar_wait(hempty_bar(hs), hphase ^ 1, p.err, 24);
-          if (elect_one()) {
+          {
             if (leader) mbar_expect_tx(hfull_bar(hs), 2u * TG2_HALO_BYTES);
             else mbar_arrive_cluster(hfull_bar(hs), 0);
             tma_load_5d_2sm(sA + hs * TG2_HALO_BYTES, &tmH, hfull_bar(hs), kc * TG_BK, a1 - 1, a2 - 1, a3, a4);
           }
-          __syncwarp();
           if (++hs == TG2_HALO_STAGES) { hs = 0; hphase ^= 1; }
-          for (int t = 0; t < p.nprim; ++t) {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {                    // halo mode: 3x3 taps, weight tap t at B coordinate (kc*64, n0, t, 0, 0)
             mbar_wait(empty_bar(stage), phase ^ 1, p.err, 21);
-            if (elect_one()) {
-              if (leader) mbar_expect_tx(full_bar(stage), 2u * b_bytes);
-              else mbar_arrive_cluster(full_bar(stage), 0);
-              tma_load_5d_2sm(sB + stage * BST, &tmB, full_bar(stage), kc * TG_BK + p.tap_b[t][0], n0,
-                              b2 + p.tap_b[t][1], b3 + p.tap_b[t][2], b4 + p.tap_b[t][3]);
-            }
-            __syncwarp();
+            if (leader) mbar_expect_tx(full_bar(stage), 2u * b_bytes);
+            else mbar_arrive_cluster(full_bar(stage), 0);
+            tma_load_5d_2sm(sB + stage * BST, &tmB, full_bar(stage), kc * TG_BK, n0, t, 0, 0);
             if (++stage == NS) { stage = 0; phase ^= 1; }
           }
         }
@@ -244,7 +244,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const CUtensorMap* tb = p.tap_src[t] ? &tmB2 : &tmB;
             mbar_wait(a2_empty_bar(s2), a2phase ^ 1, p.err, 26);
             mbar_wait(empty_bar(stage), phase ^ 1, p.err, 21);
-            if (elect_one()) {
+            {
               if (leader) mbar_expect_tx(full_bar(stage), tx_bytes);
               else mbar_arrive_cluster(full_bar(stage), 0);
               tma_load_5d_2sm(sA2 + s2 * TG_A_STAGE, ta, full_bar(stage), kc * TG_BK + p.tap_a[t][0], a1 + p.tap_a[t][1],
@@ -252,7 +252,6 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               tma_load_5d_2sm(sB + stage * BST, tb, full_bar(stage), kc * TG_BK + p.tap_b[t][0], n0,
                               b2 + p.tap_b[t][1], b3 + p.tap_b[t][2], b4 + p.tap_b[t][3]);
             }
-            __syncwarp();
             if (++stage == NS) { stage = 0; phase ^= 1; }
             if (++s2 == TG2_A2_STAGES) { s2 = 0; a2phase ^= 1; }
           }
@@ -263,12 +262,16 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int t = p.nprim; t < p.num_taps; ++t)
           for (int kc = 0; kc < p.tap_kc[t]; ++kc) load_step(t, kc);
       }
-      if (pt == cluster_id && lane == 0) tg_stamp(p, 2);   // first tile's loads all issued
+      if (pt == cluster_id) tg_stamp(p, 2);   // first tile's loads all issued
     }
-    if (lane == 0) tg_stamp(p, 3);
+    tg_stamp(p, 3);
+    }
+    __syncwarp();
   } else if (warp == TG_EPI_WARPS + 1) {
     // ================================ MMA issuer (leader CTA only) ================================
-    if (leader) {
+    // ONE elected thread runs the whole issue loop (no per-step elect / reconvergence: the loop is the critical path of the
+    // short-MMA launches, see the halo branch); the other lanes wait at the warp barrier below.
+    if (leader && elect_one()) {
       int stage = 0, phase = 0, iter = 0, hs = 0, hphase = 0;
 #ifdef I2IT_HALO_X2
       int s2 = 0;
@@ -279,27 +282,32 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * TG_ACC_COLS;
         if (p.halo) {
+          // The nine taps are unrolled with compile-time offsets into the halo tile (host order t = ky*3 + kx: tap t reads rows
+          // shifted by t/3 image rows = 2048 B and t%3 pixels = 128 B).  The r02h profile showed this single-thread loop, not
+          // operands or TMEM, bounding the N = 128 convs: ~90 instructions (parameter-table lookups, R2UR moves) per 4 MMAs
+          // of 64 cycles each = 55 % tensor pipe.
           int s = 0;
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(hfull_bar(hs), hphase, p.err, 25);
-            for (int t = 0; t < p.nprim; ++t, ++s) {
+            const uint32_t a_base = sA + hs * TG2_HALO_BYTES;
+            const bool last_kc = kc == p.kchunks - 1;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
               mbar_wait(full_bar(stage), phase, p.err, 23);
               tc_fence_after();
-              if (elect_one()) {
-                // tap (dy,dx) = rows shifted by dy image rows (2048 B) and dx pixels (128 B) inside the halo tile
-                const uint32_t dy = static_cast<uint32_t>(p.tap_a[t][2] + 1), dx = static_cast<uint32_t>(p.tap_a[t][1] + 1);
-                const uint64_t adesc = umma_desc_halo(sA + hs * TG2_HALO_BYTES + dy * 2048u + dx * 128u);
+              {
+                const uint64_t adesc = umma_desc_halo(a_base + static_cast<uint32_t>(t / 3) * 2048u + static_cast<uint32_t>(t % 3) * 128u);
                 const uint64_t bdesc = umma_desc_sw128(sB + stage * BST);
 #pragma unroll
                 for (int k = 0; k < TG_BK / 16; ++k)
-                  tc_mma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (s > 0 || k > 0) ? 1u : 0u);
+                  tc_mma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kc > 0 || t > 0 || k > 0) ? 1u : 0u);
                 tc_commit_2sm(empty_bar(stage));
-                if (t == p.nprim - 1) tc_commit_2sm(hempty_bar(hs));
-                if (s == steps - 1) tc_commit_2sm(tfull_bar(acc));
+                if (t == 8) tc_commit_2sm(hempty_bar(hs));
+                if (t == 8 && last_kc && steps == 9 * p.kchunks) tc_commit_2sm(tfull_bar(acc));
               }
-              __syncwarp();
               if (++stage == NS) { stage = 0; phase ^= 1; }
             }
+            s += 9;
             if (++hs == TG2_HALO_STAGES) { hs = 0; hphase ^= 1; }
           }
 #ifdef I2IT_HALO_X2
@@ -307,7 +315,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int kc = 0; kc < p.tap_kc[t]; ++kc, ++s) {
               mbar_wait(full_bar(stage), phase, p.err, 23);
               tc_fence_after();
-              if (elect_one()) {
+              {
                 const uint64_t adesc = umma_desc_sw128(sA2 + s2 * TG_A_STAGE);
                 const uint64_t bdesc = umma_desc_sw128(sB + stage * BST);
 #pragma unroll
@@ -317,7 +325,6 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tc_commit_2sm(a2_empty_bar(s2));
                 if (s == steps - 1) tc_commit_2sm(tfull_bar(acc));
               }
-              __syncwarp();
               if (++stage == NS) { stage = 0; phase ^= 1; }
               if (++s2 == TG2_A2_STAGES) s2 = 0;
             }
@@ -326,8 +333,8 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int s = 0; s < steps; ++s) {
             mbar_wait(full_bar(stage), phase, p.err, 23);
             tc_fence_after();
-            if (iter == 0 && s == 0 && lane == 0) tg_stamp(p, 4);               // first operands landed (both CTAs)
-            if (elect_one()) {
+            if (iter == 0 && s == 0) tg_stamp(p, 4);               // first operands landed (both CTAs)
+            {
               const uint64_t adesc = umma_desc_sw128(sA + stage * TG_A_STAGE);
               const uint64_t bdesc = umma_desc_sw128(sB + stage * BST);
 #pragma unroll
@@ -336,14 +343,14 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               tc_commit_2sm(empty_bar(stage));
               if (s == steps - 1) tc_commit_2sm(tfull_bar(acc));
             }
-            __syncwarp();
             if (++stage == NS) { stage = 0; phase ^= 1; }
           }
         }
-        if (iter == 0 && lane == 0) tg_stamp(p, 5);                             // first tile fully issued
+        if (iter == 0) tg_stamp(p, 5);                             // first tile fully issued
       }
-      if (lane == 0) tg_stamp(p, 6);
+      tg_stamp(p, 6);
     }
+    __syncwarp();
   } else if (warp < TG_EPI_WARPS) {
     // ================================ epilogue (both CTAs, own 128 rows) ================================
     const int row = (warp & 3) * 32 + lane;
@@ -352,12 +359,12 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int j2 = rr % p.box[1]; rr /= p.box[1];
     const int j3 = rr % p.box[2];
     const int j4 = rr / p.box[2];
-    int iter = 0;
+    int iter = 0, box_sel = 0;
     for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++iter) {
       const int acc = iter & 1, aphase = (iter >> 1) & 1;
       const TileCoord c = decode_pair(pt);
-      epilogue_tile<T>(p, &tmO, c, 2 * (pt / p.n_tiles) + static_cast<int>(rank), row, warp, j1, j2, j3, j4, acc, aphase,
-                       tmem_base, s_bias, ostg, tfull_bar(acc), p.n_tiles > 1 || iter < 2, iter == 0 && threadIdx.x == 0);
+      epilogue_tile<T, LEAN>(p, &tmO, c, 2 * fast_div(pt, p.n_tiles, p.magic[0]) + static_cast<int>(rank), row, warp, j1, j2, j3, j4, acc, aphase,
+                       tmem_base, s_bias, ostg, ostg2, box_sel, tfull_bar(acc), p.n_tiles > 1 || iter < 2, iter == 0 && threadIdx.x == 0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
