@@ -22,7 +22,12 @@ namespace i2it {
 
 constexpr int FA_BM = 128, FA_BN = 64, FA_D = 64, FA_STAGES = 3;
 constexpr int FA_Q_BYTES = FA_BM * FA_D * 2;            // 16 KiB
-constexpr int FA_KV_STAGE = 2 * FA_BN * FA_D * 2;       // K 8 KiB + V^T 8 KiB
+constexpr int FA_KV_DATA = 2 * FA_BN * FA_D * 2;        // K 8 KiB + V^T 8 KiB (what TMA writes per stage)
+// The PV product runs with N = 80: rows 64..79 of every V^T stage are constant — row 64 all ones, the rest zero — so column 64
+// of the O accumulator is the row sum l = sum_k P[m,k] of the ROUNDED probabilities (the same values the numerator uses); the
+// softmax threads no longer add 64 values per row and step (they are the critical path: MUFU + issue slots, profiles/r02g_flash*).
+constexpr int FA_PV_N = 80;
+constexpr int FA_KV_STAGE = FA_KV_DATA + (FA_PV_N - FA_D) * FA_BN * 2;   // + 2 KiB of constant rows
 constexpr int FA_P_BYTES = FA_BM * FA_BN * 2;           // 16 KiB
 constexpr int FA_SMEM = FA_Q_BYTES + FA_STAGES * FA_KV_STAGE + 2 * FA_P_BYTES + 256 + 1024;   // P is double-buffered
 constexpr int FA_THREADS = 192;
@@ -57,11 +62,22 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32])
         "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tc_ld1(uint32_t taddr, uint32_t (&r)[1]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_st1(uint32_t taddr, const uint32_t (&r)[1]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(r[0]) : "memory");
+}
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
 }
 __device__ __forceinline__ void sts16(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -107,6 +123,17 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmK)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmVt)) : "memory");
   }
+  if (warp < 4) {
+    // constant rows 64..79 of each stage's V^T tile (128-byte rows; all 16-byte chunks of a row are equal, so the 128B swizzle
+    // does not matter): row 64 = ones in the activation dtype, rows 65..79 = zeros
+    const uint32_t one2 = Elem<T>::pack(1.0f, 1.0f);
+    for (int i = threadIdx.x; i < FA_STAGES * (FA_PV_N - FA_D) * 8; i += 128) {
+      const int st = i / ((FA_PV_N - FA_D) * 8), r = (i / 8) % (FA_PV_N - FA_D), ch = i & 7;
+      const uint32_t v = (r == 0) ? one2 : 0u;
+      sts16(sKV + st * FA_KV_STAGE + FA_KV_DATA + r * 128 + ch * 16, v, v, v, v);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   if (warp == 5) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(tmem_slot) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -130,7 +157,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const int s = j % FA_STAGES;
       mbar_wait(kv_empty(s), ((j / FA_STAGES) & 1) ^ 1, p.err, 11);
       if (elect_one()) {
-        mbar_expect_tx(kv_full(s), FA_KV_STAGE);
+        mbar_expect_tx(kv_full(s), FA_KV_DATA);
         tma_load_5d(sKV + s * FA_KV_STAGE, &tmK, kv_full(s), 0, j * FA_BN, h, b * p.kv_bmul, 0);
         tma_load_5d(sKV + s * FA_KV_STAGE + FA_BN * FA_D * 2, &tmVt, kv_full(s), j * FA_BN, 0, h, b * p.kv_bmul, 0);
       }
@@ -140,6 +167,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     // MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma / commit
     mbar_wait(q_full, 0, p.err, 12);
     const uint64_t qdesc = umma_desc_sw128(sQ);
+    const uint32_t idesc_pv = (p.idesc & ~(0x3Fu << 17)) | (static_cast<uint32_t>(FA_PV_N >> 3) << 17);   // same shape, N = 80
     auto issue_qk = [&](int j) {
       const int s = j % FA_STAGES;
       mbar_wait(kv_full(s), (j / FA_STAGES) & 1, p.err, 13);
@@ -168,7 +196,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const uint64_t pdesc = umma_desc_sw128(sP + (j & 1) * FA_P_BYTES);
 #pragma unroll
         for (int k = 0; k < FA_BN / 16; ++k)                 // O accumulates in TMEM across the KV steps
-          tc_mma_f16(tPV, pdesc + 2 * k, vdesc + 2 * k, p.idesc, (j > 0 || k > 0) ? 1u : 0u);
+          tc_mma_f16(tPV, pdesc + 2 * k, vdesc + 2 * k, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
         tc_commit(pv_done(j & 1));
         tc_commit(kv_empty(s));                     // K_j and V_j are free once everything issued so far retires
       }
@@ -182,7 +210,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int klim = p.causal ? min(p.Nk, qpos + 1) : p.Nk;     // keys [0, klim) are visible to this row
     const float sc = p.scale_log2e;
     constexpr float TAU = 8.0f;                                  // lazy rescale: P <= 2^8 relative to the reference maximum
-    float m = -INFINITY, l = 0.f;                                // m: reference maximum (raw logit units) of this row
+    float m = -INFINITY;                                         // reference maximum (raw logit units) of this row
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(s_full(j & 1), (j >> 1) & 1, p.err, 16);
       tc_fence_after();
@@ -208,8 +236,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         for (int i = 0; i < 64; ++i)
           if (kbase + i < klim) mx = fmaxf(mx, __uint_as_float(raw[i]));
       } else {
+        // four independent chains of 3-input maxima (FMNMX3): 34 instructions instead of a 64-deep dependent chain
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4)
+            m4[c4] = fmax3(m4[c4], __uint_as_float(raw[16 * c4 + 2 * i]), __uint_as_float(raw[16 * c4 + 2 * i + 1]));
+        mx = fmax3(fmaxf(m4[0], m4[1]), m4[2], m4[3]);
       }
       const bool grow = (fmaxf(m, mx) - m) * sc > TAU;          // first tile: m = -inf -> true
       if (j == 0) {
@@ -230,17 +264,22 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
           tc_st32(tPV + lane_off + half * 32, o);
         }
+        {                                                     // ... and the row-sum column
+          uint32_t lcol[1];
+          tc_ld1(tPV + lane_off + FA_D, lcol);
+          tc_wait_ld();
+          lcol[0] = __float_as_uint(__uint_as_float(lcol[0]) * factor);
+          tc_st1(tPV + lane_off + FA_D, lcol);
+        }
         tc_wait_st();
-        l *= factor;
         m = m_new;
       }
       // P buffer j&1 was last read by PV_{j-2}
       if (j >= 2) mbar_wait(pv_done(j & 1), ((j - 2) >> 1) & 1, p.err, 19);
       const uint32_t sPj = sP + (j & 1) * FA_P_BYTES;
       const float neg_ms = -m * sc;
-      // p = exp2(s*scale - m*scale) (one FFMA + one MUFU per element), fp32 row sum of the unrounded p, pack to 16 bit, write the
+      // p = exp2(s*scale - m*scale) (one FFMA + one MUFU per element), pack to 16 bit, write the
       // swizzled K-major P tile
-      float psum = 0.f;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t pk[16];
@@ -250,7 +289,6 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             const int k0 = kbase + half * 32 + 2 * i;
             const float p0 = (k0 < klim) ? fast_exp2(fmaf(__uint_as_float(raw[half * 32 + 2 * i]), sc, neg_ms)) : 0.f;
             const float p1 = (k0 + 1 < klim) ? fast_exp2(fmaf(__uint_as_float(raw[half * 32 + 2 * i + 1]), sc, neg_ms)) : 0.f;
-            psum += p0 + p1;
             pk[i] = Elem<T>::pack(p0, p1);
           }
         } else {
@@ -258,7 +296,6 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           for (int i = 0; i < 16; ++i) {
             const float p0 = fast_exp2(fmaf(__uint_as_float(raw[half * 32 + 2 * i]), sc, neg_ms));
             const float p1 = fast_exp2(fmaf(__uint_as_float(raw[half * 32 + 2 * i + 1]), sc, neg_ms));
-            psum += p0 + p1;
             pk[i] = Elem<T>::pack(p0, p1);
           }
         }
@@ -268,7 +305,6 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           sts16(sPj + row * 128 + ((gg ^ (row & 7)) << 4), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
         }
       }
-      l += psum;
       // P_j visible to the async proxy (and any O rescale complete) -> PV_j may start
       tc_fence_before();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -279,7 +315,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     mbar_wait(pv_done((nkv - 1) & 1), ((nkv - 1) >> 1) & 1, p.err, 18);
     tc_fence_after();
     const int q = qt * FA_BM + row;
-    const float inv = 1.0f / l;
+    float inv;
+    {
+      uint32_t lcol[1];
+      tc_ld1(tPV + lane_off + FA_D, lcol);
+      tc_wait_ld();
+      inv = 1.0f / __uint_as_float(lcol[0]);
+    }
     T* optr = reinterpret_cast<T*>(p.out) + (static_cast<long long>(b) * p.Nq + q) * p.ldo + h * FA_D;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {

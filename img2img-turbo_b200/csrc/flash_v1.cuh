@@ -66,7 +66,7 @@ flash_attn_v1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const int s = j % FA_STAGES;
       mbar_wait(kv_empty(s), ((j / FA_STAGES) & 1) ^ 1, p.err, 11);
       if (elect_one()) {
-        mbar_expect_tx(kv_full(s), FA_KV_STAGE);
+        mbar_expect_tx(kv_full(s), FA_KV_DATA);      // (the stage stride also holds the current kernel's 2 KB of constant rows)
         tma_load_5d(sKV + s * FA_KV_STAGE, &tmK, kv_full(s), 0, j * FA_BN, h, b * p.kv_bmul, 0);
         tma_load_5d(sKV + s * FA_KV_STAGE + FA_BN * FA_D * 2, &tmVt, kv_full(s), j * FA_BN, 0, h, b * p.kv_bmul, 0);
       }

@@ -27,13 +27,15 @@ constexpr int TG2_HALO_BYTES = TG2_HALO_H * TG2_HALO_W * TG_BK * 2;   // 36,864
 constexpr int TG2_HALO_STAGES = 2;
 constexpr int TG2_A2_STAGES = 2;
 #else
-constexpr int TG2_HALO_STAGES = 2;   // two 36 KB halo tiles (each serves nine taps) leave room for the 32 KB of epilogue store boxes
+#ifndef I2IT_HALO_STAGES
+#define I2IT_HALO_STAGES 2           // `make HALO3=1` builds a three-halo-stage library for A/B runs (fewer B stages)
+#endif
+constexpr int TG2_HALO_STAGES = I2IT_HALO_STAGES;   // two 36 KB halo tiles (each serves nine taps) leave room for the 32 KB of epilogue store boxes
 constexpr int TG2_A2_STAGES = 0;
 #endif
 constexpr int TG2_HALO_REGION = TG2_HALO_STAGES * TG2_HALO_BYTES + TG2_A2_STAGES * TG_A_STAGE;   // [halo stages][A2 stages]
-constexpr int TG2_DATA_BYTES = (TG2_STAGES * (TG_A_STAGE + TG2_B_STAGE) > TG2_HALO_REGION + TG2_STAGES * TG2_B_STAGE)
-                                   ? TG2_STAGES * (TG_A_STAGE + TG2_B_STAGE)
-                                   : TG2_HALO_REGION + TG2_STAGES * TG2_B_STAGE;
+constexpr int TG2_DATA_BYTES = TG2_STAGES * (TG_A_STAGE + TG2_B_STAGE);   // 192 KB; halo mode: [halo region][B stages in the rest]
+static_assert(TG2_HALO_REGION + 4 * TG2_B_STAGE <= TG2_DATA_BYTES, "halo region leaves fewer than four full B stages");
 constexpr int TG2_SMEM = TG2_DATA_BYTES + TG_BAR_BYTES + TG_BIAS_BYTES + TG_OSTG_BYTES + TG_ALIGN_PAD;
 static_assert(TG_SMEM <= 232448 && TG2_SMEM <= 232448, "dynamic shared memory per CTA exceeds the 227 KB limit");
 

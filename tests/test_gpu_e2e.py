@@ -223,7 +223,8 @@ def test_runtime_switches_agree(monkeypatch):
     args = (x.to(dt).cuda(), text[:1].to(dt).cuda(), eps.to(dt).cuda())
 
     def run(**env):
-        for k in ("I2IT_NO_CATFUSE", "I2IT_NO_TMAOUT", "I2IT_NO_GNEPI", "I2IT_NO_SPLITK", "I2IT_FLASH_V1", "I2IT_NO_IDRES",
+        for k in ("I2IT_NO_CATFUSE", "I2IT_NO_TMAOUT", "I2IT_NO_GNEPI", "I2IT_NO_SPLITK", "I2IT_FLASH_V1", "I2IT_NO_IDRES", "I2IT_IDRES",
+                  "I2IT_NO_LEAN", "I2IT_NO_OSTG2",
                   "I2IT_NO_HALO", "I2IT_NO_PAIR"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
@@ -235,8 +236,10 @@ def test_runtime_switches_agree(monkeypatch):
         return y
     base = run()
     assert torch.equal(base, run(I2IT_NO_CATFUSE="1"))
+    assert torch.equal(base, run(I2IT_NO_LEAN="1"))            # the compile-time-stripped epilogue computes the same bits
+    assert torch.equal(base, run(I2IT_NO_OSTG2="1"))           # one or two store boxes: data movement only
     assert torch.equal(run(I2IT_NO_GNEPI="1"), run(I2IT_NO_GNEPI="1", I2IT_NO_TMAOUT="1"))
-    for env in ({"I2IT_NO_GNEPI": "1"}, {"I2IT_NO_SPLITK": "1"}, {"I2IT_FLASH_V1": "1"}, {"I2IT_NO_IDRES": "1"},
+    for env in ({"I2IT_NO_GNEPI": "1"}, {"I2IT_NO_SPLITK": "1"}, {"I2IT_FLASH_V1": "1"}, {"I2IT_IDRES": "1"},
                 {"I2IT_NO_HALO": "1"}, {"I2IT_NO_PAIR": "1"}):
         y = run(**env)
         d = (y.float() - base.float()).abs()
