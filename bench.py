@@ -221,9 +221,58 @@ class Workload:
                          r=self.r if self.stochastic else 1.0, direction=self.direction, out=self.out, out_latent=self.lat)
 
 
-def timed(step_fn, K, Wm, world, dist, flush):
+def make_step(w, world, dist):
+    """The timed step of one workload on this rank: the engine-level forward plus, at N > 1, the single collective
+    (all-gather of the output latents, 32 KB per image).  Returns (step, finish, description).
+
+    Default: the collective is issued on the compute stream after every step.  I2IT_OVERLAP_GATHER=1 issues it on a SIDE stream
+    so that step i+1 computes while the all-gather of step i is in flight (two alternating latent / gather buffers; a step
+    waits for the gather that read its buffer two steps back; `finish` joins the side stream into the timed stream before the
+    closing event, so all K collectives complete inside the timed region).  Measured on 2 x B200 (round 2, runs E, DESIGN
+    section 5): both variants cost the same 1.4-2.0 ms per 36.5 ms step although the all-gather alone takes 15 us — the loss is
+    the per-step synchronisation of GPUs whose step times differ (power capping: 2 % between GPUs, sigma 0.7-1.0 ms per step),
+    not the transfer — so the simpler synchronous form stays the default."""
+    if world == 1:
+        return w.step, None, "none"
+    B, S, dt = w.B, w.S, w.dt
+    if os.environ.get("I2IT_OVERLAP_GATHER") is None:
+        gathered = torch.empty(world * B, 4, S // 8, S // 8, device="cuda", dtype=dt)
+
+        def step_sync():
+            w.step()
+            dist.all_gather_into_tensor(gathered, w.lat)              # the single collective: output latents over NVLink
+        return step_sync, None, "all_gather_into_tensor(output latents) on the compute stream"
+    side = torch.cuda.Stream()
+    lats = [w.lat, torch.empty_like(w.lat)]
+    gath = [torch.empty(world * B, 4, S // 8, S // 8, device="cuda", dtype=dt) for _ in range(2)]
+    gdone = [None, None]
+    cnt = [0]
+
+    def step():
+        i = cnt[0] & 1
+        cur = torch.cuda.current_stream()
+        if gdone[i] is not None:
+            cur.wait_event(gdone[i])
+        w.lat = lats[i]
+        w.step()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        with torch.cuda.stream(side):
+            side.wait_event(ev)
+            dist.all_gather_into_tensor(gath[i], lats[i])
+            gdone[i] = torch.cuda.Event()
+            gdone[i].record(side)
+        cnt[0] += 1
+
+    def finish():
+        torch.cuda.current_stream().wait_stream(side)
+    return step, finish, "all_gather_into_tensor(output latents) on a side stream, overlapped with the next step"
+
+
+def timed(step_fn, K, Wm, world, dist, flush, finish=None):
     """W warm-up steps, then K steps bracketed by barrier + synchronize, CUDA events, MAX over ranks.  Returns
-    (ms_per_step_max_over_ranks, this rank's ms_per_step)."""
+    (ms_per_step_max_over_ranks, this rank's ms_per_step).  `finish` joins side streams (the overlapped collective) into the
+    timed stream before the closing event, so every collective of the K steps completes inside the timed region."""
     for _ in range(Wm):
         flush.zero_()
         step_fn()
@@ -236,6 +285,8 @@ def timed(step_fn, K, Wm, world, dist, flush):
     for _ in range(K):
         flush.zero_()                                                  # L2 flush between iterations
         step_fn()
+    if finish is not None:
+        finish()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -299,13 +350,8 @@ def main():
     build_s = {"weights_init_s": round(wl.t_weights, 2), "engine_upload_fold_plan_first_forward_s": round(wl.t_engine, 2),
                "prep_launches": eng.prep_launch_count()}
 
-    gathered = torch.empty(world * B, 4, S // 8, S // 8, device="cuda", dtype=dt) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
-
-    def step():
-        wl.step()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, wl.lat)              # the single collective: output latents over NVLink
+    step, finish, collective = make_step(wl, world, dist)
 
     sampler = ClockSampler(local)
     sampler.start()                      # before the warm-up: its start-up cost stays out of the timed region
@@ -314,7 +360,9 @@ def main():
         step()
     torch.cuda.synchronize()
     sampler.mark()
-    ms_step, ms_mine = timed(step, K, 0, world, dist, flush)
+    if finish is not None:
+        finish()
+    ms_step, ms_mine = timed(step, K, 0, world, dist, flush, finish)
     clocks = sampler.stop()
     value = world * B / (ms_step / 1e3)
     finite = bool(torch.isfinite(wl.out.float()).all().item())
@@ -393,13 +441,11 @@ def main():
             rows = []
             for b in sweep:
                 w2.set_batch(b)
-                g2 = torch.empty(world * b, 4, S // 8, S // 8, device="cuda", dtype=w2.dt) if world > 1 else None
-
-                def step2():
-                    w2.step()
-                    if world > 1:
-                        dist.all_gather_into_tensor(g2, w2.lat)
-                ms2, _ = timed(step2, Kx, 3, world, dist, flush)
+                step2, fin2, _ = make_step(w2, world, dist)
+                ms2, _ = timed(step2, Kx, 3, world, dist, flush, fin2)
+                if fin2 is not None:
+                    fin2()
+                    torch.cuda.synchronize()
                 rows.append({"per_gpu_batch": b, "global_batch": world * b, "value": world * b / (ms2 / 1e3), "ms_per_step": ms2,
                              "finite": bool(torch.isfinite(w2.out.float()).all().item()),
                              "step_tensor_frac_of_sustained_peak": (b * FLOPS_PER_IMAGE / (ms2 * 1e-3)) / 1e12 / measured_peaks()[0]})
@@ -473,7 +519,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload, "per_gpu_batch": B, "global_batch": world * B, "size": S,
                        "parallelism": f"dp{world}", "l2": "256 MiB flush write between timed iterations",
-                       "collective": "1 x all_gather_into_tensor(output latents) per step" if world > 1 else "none",
+                       "collective": ("1 x " + collective + " per step") if world > 1 else "none",
                        "cuda_graph": True, "text": "prompt K/V projected once per prompt (i2it_set_text), not per step"},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes,
                     "api": "model(c_t, prompt) — the reference's call; pinned host tensor in, pinned host tensor out"},
