@@ -129,6 +129,7 @@ Engine::Engine(const i2it_config& c) : cfg(c), dtype(c.dtype) {
 #endif
   use_tmaout = std::getenv("I2IT_NO_TMAOUT") == nullptr;   // TMA-store epilogue (per-thread stores otherwise)
   use_ostg2 = std::getenv("I2IT_NO_OSTG2") == nullptr;     // second TMA-store box per epilogue warp where the operand ring can spare 32 KB
+  sync_each = std::getenv("I2IT_SYNC_EACH") != nullptr;    // eager path: synchronise after every launch and name the one that faults
   use_lean = std::getenv("I2IT_NO_LEAN") == nullptr;       // compile-time-stripped epilogue for the plain (no activation) TMA-store launches
   use_gnepi = std::getenv("I2IT_NO_GNEPI") == nullptr;     // GroupNorm statistics in the producing GEMM's epilogue
   use_splitk = std::getenv("I2IT_NO_SPLITK") == nullptr;   // split-K for the 8x8 1280-channel convs
@@ -1441,6 +1442,11 @@ void Engine::forward(const IO& io_in, int B, int H, int W, int direction, int te
         ++next_range;
       }
       P->ops[i](st);
+      if (sync_each) {   // I2IT_SYNC_EACH=1 (debugging): attribute an asynchronous fault to the launch that caused it
+        const cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess)
+          throw Error("launch " + std::to_string(i) + " (" + P->meta[i].kind + " " + P->meta[i].shape + "): " + cudaGetErrorString(e));
+      }
     }
     if (open) nvtxRangePop();
     I2IT_CUDA(cudaGetLastError());

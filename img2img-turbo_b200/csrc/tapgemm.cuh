@@ -697,8 +697,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (TG_REGS_EPI > 0) { if (warp >= TG_EPI_WARPS) reg_dec<TG_REGS_CTRL>(); else reg_inc<TG_REGS_EPI>(); }
 
   if (warp == TG_EPI_WARPS) {
-    // ================================ TMA producer: ONE elected thread runs the whole loop ==========
-    if (elect_one()) {
+    // ================================ TMA producer (whole warp runs the loop, one elected lane issues) ==========
+    // (the single-thread form of the CTA-pair kernel is NOT used here: with it this kernel faulted sporadically in the
+    // timeline-stamp build — different launches each time, clean under compute-sanitizer — so it keeps the round-1 form)
     int stage = 0, phase = 0;
     const uint32_t tx_bytes = TG_A_STAGE + static_cast<uint32_t>(p.BN) * (TG_BK * 2);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -711,13 +712,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const CUtensorMap* ta = p.tap_src[t] ? &tmA2 : &tmA;
         const CUtensorMap* tb = p.tap_src[t] ? &tmB2 : &tmB;
         mbar_wait(empty_bar(stage), phase ^ 1, p.err, 1);
-        {
+        if (elect_one()) {
           mbar_expect_tx(full_bar(stage), tx_bytes);
           tma_load_5d(sA + stage * TG_A_STAGE, ta, full_bar(stage), kc * TG_BK + p.tap_a[t][0],
                       a1 + p.tap_a[t][1], a2 + p.tap_a[t][2], a3 + p.tap_a[t][3], a4 + p.tap_a[t][4]);
           tma_load_5d(sB + stage * BST, tb, full_bar(stage), kc * TG_BK + p.tap_b[t][0], n0,
                       b2 + p.tap_b[t][1], b3 + p.tap_b[t][2], b4 + p.tap_b[t][3]);
         }
+        __syncwarp();
         if (++stage == NS) { stage = 0; phase ^= 1; }
       };
       const int kc0 = nsplit > 1 ? c.split * p.kc_per : 0, kc1 = nsplit > 1 ? min(p.kchunks, kc0 + p.kc_per) : p.kchunks;
@@ -726,15 +728,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (c.split == 0)
         for (int t = p.nprim; t < p.num_taps; ++t)
           for (int kc = 0; kc < p.tap_kc[t]; ++kc) load_step(t, kc);
-      if (tile == static_cast<int>(blockIdx.x)) tg_stamp(p, 2);   // first tile's loads all issued
+      if (tile == static_cast<int>(blockIdx.x) && lane == 0) tg_stamp(p, 2);   // first tile's loads all issued
     }
-    tg_stamp(p, 3);
-    }
-    __syncwarp();
+    if (lane == 0) tg_stamp(p, 3);
   } else if (warp == TG_EPI_WARPS + 1) {
-    // ================================ MMA issuer: ONE elected thread runs the whole loop ================================
-    // (no per-step elect / reconvergence: for the short MMAs, BN <= 128, the issue loop itself is the critical path — r02h)
-    if (elect_one()) {
+    // ================================ MMA issuer (warp-uniform loop, elected lane issues) ================================
     int stage = 0, phase = 0, iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       const int acc = iter & 1, aphase = (iter >> 1) & 1;
@@ -750,8 +748,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int s = 0; s < tsteps; ++s) {
         mbar_wait(full_bar(stage), phase, p.err, 3);
         tc_fence_after();
-        if (iter == 0 && s == 0) tg_stamp(p, 4);                                // first operands landed
-        {
+        if (iter == 0 && s == 0 && lane == 0) tg_stamp(p, 4);                   // first operands landed
+        if (elect_one()) {
           const uint64_t adesc = umma_desc_sw128(sA + stage * TG_A_STAGE);
           const uint64_t bdesc = umma_desc_sw128(sB + stage * BST);
 #pragma unroll
@@ -760,13 +758,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_commit(empty_bar(stage));               // frees the smem slot when these MMAs retire
           if (s == tsteps - 1) tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
         }
+        __syncwarp();
         if (++stage == NS) { stage = 0; phase ^= 1; }
       }
-      if (iter == 0) tg_stamp(p, 5);                                            // first tile fully issued
+      if (iter == 0 && lane == 0) tg_stamp(p, 5);                               // first tile fully issued
     }
-    tg_stamp(p, 6);
-    }
-    __syncwarp();
+    if (lane == 0) tg_stamp(p, 6);
   } else if (warp < TG_EPI_WARPS) {
     // ================================ epilogue (warps 0..7) ================================
     const int row = (warp & 3) * 32 + lane;
