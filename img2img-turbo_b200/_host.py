@@ -152,6 +152,10 @@ class TurboBase(torch.nn.Module):
     MODEL_KIND = i2it.PIX2PIX
 
     def _init_common(self, cfg, dtype, text_stack, use_cuda_graph=True, keep_stages=False):
+        # I2IT_CFG=tiny: reduced-width network when the caller cannot pass `cfg` — the unmodified reference CLIs in the test suite
+        # (tests/test_reference_cli.py); the default is always the SD-Turbo geometry
+        if cfg is None and os.environ.get("I2IT_CFG") == "tiny":
+            cfg = W.TINY
         self._cfg = cfg or W.SD_TURBO
         self._dtype = dtype                      # None until .half()/.bfloat16()/.to(dtype); engine default bf16
         self._engine: Optional[i2it.Engine] = None

@@ -20,6 +20,7 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree n
 def _run(script, args, cwd, timeout=900):
     env = dict(os.environ)
     env["PYTHONPATH"] = ""
+    env["I2IT_CFG"] = "tiny"        # the CLI cannot pass a reduced config: the drop-in modules take it from the environment
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "run_reference_cli.py"), os.path.join(REF, script)] + args,
                        capture_output=True, text=True, cwd=cwd, env=env, timeout=timeout)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
@@ -41,7 +42,7 @@ def test_inference_paired_unmodified(tmp_path):
 
     class Tok:
         model_max_length = 77
-    m = Pix2Pix_Turbo(text_stack=(Tok(), None), seed=3)          # full SD-Turbo widths: the CLI cannot pass a reduced config
+    m = Pix2Pix_Turbo(cfg=W.TINY, text_stack=(Tok(), None), seed=3)   # reduced widths (I2IT_CFG=tiny on the CLI side): CPU minutes, not hours
     ck = str(tmp_path / "model.pkl")
     m.save_model(ck)
     _png(str(tmp_path / "in.png"), 70, 66, 1)                     # 70x66 -> cropped to 64x64 by the script (multiples of 8)
@@ -66,7 +67,8 @@ def test_inference_unpaired_unmodified(tmp_path):
 
     class Tok:
         model_max_length = 77
-    m = CycleGAN_Turbo(text_stack=(Tok(), None), synthetic_caption="c", synthetic_direction="a2b", seed=4)
+    import weights as W
+    m = CycleGAN_Turbo(cfg=W.TINY, text_stack=(Tok(), None), synthetic_caption="c", synthetic_direction="a2b", seed=4)
     # the checkpoint format written by train_cyclegan_turbo.py:293-307
     def part(adapter):
         return {k[len("unet."):].replace(f".{adapter}.weight", ".weight"): v for k, v in m._sd.items()
