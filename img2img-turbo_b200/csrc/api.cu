@@ -139,6 +139,13 @@ int i2it_forward_u8(i2it_handle* h, const void* x_u8_hwc, int in_mode, const voi
   API_END
 }
 
+long long i2it_debug_fast_div(long long max_dividend, int d, int x) {
+  const uint32_t m = i2it::make_magic(max_dividend, d);              // the host function launch_gemm uses
+  if (m == 0) return -1;
+  if (d == 1) return x;                                              // fast_div selects x for d == 1
+  return static_cast<long long>((static_cast<unsigned long long>(static_cast<uint32_t>(x)) * m) >> 32);   // == __umulhi(x, m)
+}
+
 int i2it_prep_launch_count(i2it_handle* h, int* launches) {
   API_BEGIN(h)
   I2IT_CHECK(launches != nullptr, "null out pointer");

@@ -28,7 +28,7 @@ _DT2TORCH = {F16: torch.float16, BF16: torch.bfloat16}
 SYMBOLS = [
     "i2it_default_config", "i2it_create", "i2it_destroy", "i2it_last_error", "i2it_set_weight",
     "i2it_set_adapter_scale", "i2it_finalize_weights", "i2it_workspace_bytes", "i2it_forward",
-    "i2it_set_text", "i2it_encode_text", "i2it_forward_u8", "i2it_prep_launch_count", "i2it_launch_count", "i2it_profile", "i2it_read_stage", "i2it_op_conv2d", "i2it_op_group_norm", "i2it_op_layer_norm",
+    "i2it_set_text", "i2it_encode_text", "i2it_forward_u8", "i2it_prep_launch_count", "i2it_debug_fast_div", "i2it_launch_count", "i2it_profile", "i2it_read_stage", "i2it_op_conv2d", "i2it_op_group_norm", "i2it_op_layer_norm",
     "i2it_op_attention", "i2it_op_upsample2x",
 ]
 
@@ -73,6 +73,8 @@ def load_library(path: Optional[str] = None):
     lib.i2it_encode_text.argtypes = [vp, vp, ci, vp, vp]
     lib.i2it_forward_u8.argtypes = [vp, vp, ci, vp, ci, vp, vp, cf, vp, vp, ci, ci, ci, ci, vp]
     lib.i2it_prep_launch_count.argtypes = [vp, C.POINTER(ci)]
+    lib.i2it_debug_fast_div.argtypes = [C.c_longlong, ci, ci]
+    lib.i2it_debug_fast_div.restype = C.c_longlong
     lib.i2it_launch_count.argtypes = [vp, ci, ci, ci, ci, C.POINTER(ci)]
     lib.i2it_profile.argtypes = [vp, ci, C.c_char_p, C.c_size_t, vp]
     lib.i2it_read_stage.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(ci)]

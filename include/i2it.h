@@ -137,6 +137,11 @@ int i2it_launch_count(i2it_handle* h, int batch, int H, int W, int direction, in
  * created: a job table makes this 4-5 per finalize+plan instead of one to four per tensor. */
 int i2it_prep_launch_count(i2it_handle* h, int* launches);
 
+/* Host-side check of the division-free tile decode the GEMM kernels use (csrc/tapgemm.cuh: make_magic / fast_div): returns the
+ * quotient the device computes for x / d (magic made for dividends <= max_dividend, 32-bit high multiply), or -1 when the host
+ * would refuse that tile space.  No GPU needed: lets the CPU test suite pin the index arithmetic bit for bit. */
+long long i2it_debug_fast_div(long long max_dividend, int d, int x);
+
 /* Per-launch device timing of the plan the LAST forward used: runs it `reps` more times with CUDA events around
  * every launch and writes a JSON array [{"i","kind","ms","flops","bytes","shape"}...] (algorithmic flops/bytes per
  * launch) into `json`.  Synchronous.  This is what bench.py's roofline numbers are computed from. */

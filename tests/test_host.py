@@ -315,3 +315,30 @@ def test_fp32_model_warns_that_it_computes_in_bf16():
         assert m.compute_dtype == torch.bfloat16
     m.half()
     assert m.compute_dtype == torch.float16
+
+
+def test_tile_decode_magic_division_is_exact():
+    """The GEMM kernels decode tile indices with host-made magic numbers (csrc/tapgemm.cuh: make_magic / fast_div: one 32-bit
+    high multiply instead of an integer division).  Index arithmetic must be exact: every divisor the plans use (n-tiles, tile
+    counts per dimension) against every dividend below the tile-space bound, through the library's own host function."""
+    import random
+    import i2it
+    lib = i2it.load_library()
+    rng = random.Random(0)
+    # (max dividend, divisor): tile spaces of the path — 16384 m-tiles x 2 n-tiles (+ grid), token matrices of 32768 / 128 rows,
+    # batch 128 sweeps, and adversarial divisors around powers of two
+    cases = [(2 * 16384 + 2 + 148, d) for d in (1, 2, 3, 5, 7, 8, 9, 16, 31, 32, 33, 64, 74, 127, 128, 148, 160, 255, 256, 257, 4096)]
+    cases += [(8 * 2 * 16384 + 150, d) for d in (2, 3, 6, 10, 100, 1000, 1023, 1025, 8191, 8193, 16384)]
+    for maxd, d in cases:
+        xs = {0, 1, d - 1, d, d + 1, maxd - 1, maxd // 2} | {rng.randrange(maxd) for _ in range(400)} | {k * d - 1 for k in range(1, 40)} | \
+             {k * d for k in range(1, 40)}
+        refused = d > 1 and maxd * d >= (1 << 32)          # the host raises for such a tile space instead of decoding wrongly
+        for x in xs:
+            if 0 <= x < maxd:
+                assert lib.i2it_debug_fast_div(maxd, d, x) == (-1 if refused else x // d), (maxd, d, x)
+    # exhaustive for one real launch: 16384 m-tiles, pair kernel dividends up to 2 * m_tiles + 2 + grid
+    maxd = 2 * 16384 + 2 + 148
+    for d in (2, 32, 128):
+        assert all(lib.i2it_debug_fast_div(maxd, d, x) == x // d for x in range(maxd))
+    # tile spaces too large for the 32-bit magic are refused (the host raises instead of decoding wrongly)
+    assert lib.i2it_debug_fast_div(1 << 31, 3, 5) == -1
